@@ -1,0 +1,643 @@
+// zpq_abi.cu -- C ABI (include/zpq.h) over the kernels: context, batching of
+// independent archive blocks, host<->device staging, per-block status.
+//
+// There is NO CPU implementation of the coding path in this library: every
+// entry point that codes data launches zpq_code_kernel and fails with
+// ZPQ_E_CUDA when no device is usable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <chrono>
+#include <string.h>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+#include "zpq_host.h"
+#include "zpq_kernels.h"
+
+using namespace zpq;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr; uint64_t cap = 0;
+  cudaError_t reserve(uint64_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const uint64_t want = n + (n >> 3) + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, n); if (e == cudaSuccess) cap = n; return e; }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Piece { const uint8_t* p; uint64_t n; };
+
+struct IJob {
+  const uint8_t* hdr = nullptr; int hlen = 0;
+  std::vector<Piece> in;             // input pieces, concatenated on the device
+  std::vector<uint64_t> seg_len;
+  uint8_t* out = nullptr; uint64_t out_cap = 0;
+  uint64_t out_skip = 0;             // leading device-output bytes not copied to `out`
+  std::vector<uint64_t> seg_out;
+  uint64_t out_len = 0;
+  int status = ZPQ_OK;
+  int first_byte = -1;
+  // filled by run_batch
+  int model = -1;
+  uint64_t in_total = 0;
+};
+
+}  // namespace
+
+struct zpq_ctx {
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr; bool own_stream = true;
+  ZTables* d_tables = nullptr;
+  void* ws = nullptr; uint64_t ws_bytes = 0; bool own_ws = true;
+  DevBuf d_in, d_out, d_meta;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  float ms[3] = {0, 0, 0};
+  uint64_t launches = 0;
+};
+
+namespace {
+
+int cuda_fail(zpq_ctx* c, cudaError_t e, const char* what) {
+  char buf[256];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  if (c) c->err = buf;
+  cudaGetLastError();
+  return ZPQ_E_CUDA;
+}
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, what); } while (0)
+
+uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// Run one batch of independent blocks through the GPU.
+int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
+  if (!ctx) return ZPQ_E_ARG;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  ctx->ms[0] = ctx->ms[1] = ctx->ms[2] = 0;
+  const int nj = (int)jobs.size();
+  if (nj == 0) return ZPQ_OK;
+  const auto t_begin = std::chrono::steady_clock::now();
+
+  // ---- compile models (shared by blocks with identical headers) ----
+  std::vector<ZModel> models;
+  std::vector<uint8_t> progs;
+  std::map<std::string, int> seen;     // header bytes -> model index, or -1 - (error code) for a header that failed
+  for (int i = 0; i < nj; ++i) {
+    IJob& J = jobs[i];
+    J.status = ZPQ_OK; J.out_len = 0; J.first_byte = -1;
+    J.seg_out.assign(J.seg_len.size(), 0);
+    J.in_total = 0;
+    for (const Piece& pc : J.in) J.in_total += pc.n;
+    uint64_t segsum = 0;
+    for (uint64_t s : J.seg_len) segsum += s;
+    if (!J.hdr || J.hlen <= 0 || J.seg_len.empty() || segsum != J.in_total || (dev_io && J.in.size() != 1)) {
+      J.status = ZPQ_E_ARG; continue;
+    }
+    std::string key((const char*)J.hdr, (size_t)J.hlen);
+    auto it = seen.find(key);
+    if (it != seen.end()) {
+      if (it->second >= 0) J.model = it->second;
+      else { J.model = -1; J.status = it->second + 1; }     // undo the -1 - code encoding (codes are negative)
+      continue;
+    }
+    ZModel M; std::vector<uint8_t> image; std::string e;
+    const int rc = compile_model(J.hdr, J.hlen, &M, &image, &e);
+    if (rc != ZPQ_OK) { J.status = rc; ctx->err = e; seen[key] = rc - 1; J.model = -1; continue; }
+    M.prog_off = (uint32_t)progs.size();
+    progs.insert(progs.end(), image.begin(), image.end());
+    while (progs.size() & 15) progs.push_back(0);
+    J.model = (int)models.size();
+    seen[key] = J.model;
+    models.push_back(M);
+  }
+  std::vector<int> todo;
+  for (int i = 0; i < nj; ++i) if (jobs[i].status == ZPQ_OK && jobs[i].model >= 0) todo.push_back(i);
+  if (todo.empty()) return ZPQ_OK;
+
+  // ---- workspace for the model arenas ----
+  uint64_t need_all = 0, need_max = 0;
+  for (int i : todo) {
+    const uint64_t a = models[jobs[i].model].arena_bytes;
+    need_all += a; need_max = std::max(need_max, a);
+  }
+  if (ctx->own_ws && ctx->ws_bytes < need_all) {
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot), "cudaMemGetInfo");
+    const uint64_t avail = (uint64_t)fr + ctx->ws_bytes;
+    const uint64_t reserve = (uint64_t)3 << 30;     // staging buffers, CUDA context
+    uint64_t want = std::min(need_all, avail > reserve ? avail - reserve : 0);
+    if (want > ctx->ws_bytes) {
+      if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+      cudaError_t e = cudaMalloc(&ctx->ws, want);
+      if (e != cudaSuccess) { cudaGetLastError(); want = std::min(want, std::max(need_max, want / 2)); e = cudaMalloc(&ctx->ws, want); }
+      if (e != cudaSuccess) { cuda_fail(ctx, e, "workspace cudaMalloc"); for (int i : todo) jobs[i].status = ZPQ_E_NOMEM; return ZPQ_E_NOMEM; }
+      ctx->ws_bytes = want;
+    }
+  }
+  if (ctx->ws_bytes < need_max) {
+    for (int i : todo) if (models[jobs[i].model].arena_bytes > ctx->ws_bytes) jobs[i].status = ZPQ_E_NOMEM;
+    ctx->err = "Out of memory";
+  }
+
+  cudaEvent_t* ev = ctx->ev;
+  float ms_init = 0, ms_code = 0, ms_all = 0;
+  size_t next = 0;
+  while (next < todo.size()) {
+    // ---- one wave: as many blocks as the workspace holds ----
+    std::vector<int> wave;
+    uint64_t used = 0;
+    while (next < todo.size()) {
+      IJob& J = jobs[todo[next]];
+      if (J.status != ZPQ_OK) { ++next; continue; }
+      const uint64_t a = models[J.model].arena_bytes;
+      if (used + a > ctx->ws_bytes) break;
+      used += a; wave.push_back(todo[next]); ++next;
+    }
+    if (wave.empty()) { if (next < todo.size()) continue; break; }
+    const int nb = (int)wave.size();
+
+    std::vector<ZBlock> blocks(nb);
+    std::vector<uint64_t> seg_len;
+    uint64_t in_bytes = 0, out_bytes = 0, arena = 0;
+    for (int k = 0; k < nb; ++k) {
+      IJob& J = jobs[wave[k]];
+      ZBlock& B = blocks[k];
+      B.model = (uint32_t)J.model;
+      B.seg_first = (uint32_t)seg_len.size(); B.nseg = (uint32_t)J.seg_len.size(); B.pad = 0;
+      seg_len.insert(seg_len.end(), J.seg_len.begin(), J.seg_len.end());
+      B.arena_off = arena; arena += models[J.model].arena_bytes;
+      if (dev_io) {
+        B.in_off = (uint64_t)(uintptr_t)J.in[0].p;
+        B.out_off = (uint64_t)(uintptr_t)J.out;
+        B.out_cap = J.out_cap;
+      } else {
+        B.in_off = in_bytes; in_bytes = align_up(in_bytes + J.in_total, 16);
+        B.out_off = out_bytes; B.out_cap = J.out_cap + J.out_skip;
+        out_bytes = align_up(out_bytes + B.out_cap, 16);
+      }
+    }
+    const int nseg = (int)seg_len.size();
+
+    if (!dev_io) {
+      CK(ctx->d_in.reserve(in_bytes + 16), "input staging cudaMalloc");
+      CK(ctx->d_out.reserve(out_bytes + 16), "output staging cudaMalloc");
+    }
+    // meta: models | blocks | progs | seg_len | seg_out | status | out_len | first | counter
+    uint64_t off = 0;
+    const uint64_t o_models = off; off = align_up(off + models.size() * sizeof(ZModel), 256);
+    const uint64_t o_blocks = off; off = align_up(off + (uint64_t)nb * sizeof(ZBlock), 256);
+    const uint64_t o_progs = off;  off = align_up(off + progs.size(), 256);
+    const uint64_t o_seglen = off; off = align_up(off + (uint64_t)nseg * 8, 256);
+    const uint64_t o_segout = off; off = align_up(off + (uint64_t)nseg * 8, 256);
+    const uint64_t o_status = off; off = align_up(off + (uint64_t)nb * 4, 256);
+    const uint64_t o_outlen = off; off = align_up(off + (uint64_t)nb * 8, 256);
+    const uint64_t o_counter = off; off = align_up(off + 4, 256);
+    CK(ctx->d_meta.reserve(off), "meta cudaMalloc");
+    uint8_t* dm = (uint8_t*)ctx->d_meta.p;
+    cudaStream_t st = ctx->stream;
+
+    CK(cudaMemcpyAsync(dm + o_models, models.data(), models.size() * sizeof(ZModel), cudaMemcpyHostToDevice, st), "H2D models");
+    CK(cudaMemcpyAsync(dm + o_blocks, blocks.data(), (size_t)nb * sizeof(ZBlock), cudaMemcpyHostToDevice, st), "H2D blocks");
+    CK(cudaMemcpyAsync(dm + o_progs, progs.data(), progs.size(), cudaMemcpyHostToDevice, st), "H2D programs");
+    CK(cudaMemcpyAsync(dm + o_seglen, seg_len.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, st), "H2D segments");
+    CK(cudaMemsetAsync(dm + o_segout, 0, (size_t)(o_counter + 256 - o_segout), st), "memset");
+    if (!dev_io) {
+      for (int k = 0; k < nb; ++k) {
+        IJob& J = jobs[wave[k]];
+        uint64_t at = blocks[k].in_off;
+        for (const Piece& pc : J.in) {
+          if (pc.n) CK(cudaMemcpyAsync((uint8_t*)ctx->d_in.p + at, pc.p, pc.n, cudaMemcpyHostToDevice, st), "H2D input");
+          at += pc.n;
+        }
+      }
+    }
+
+    ZKernelArgs A;
+    A.models = (const ZModel*)(dm + o_models);
+    A.blocks = (const ZBlock*)(dm + o_blocks);
+    A.progs = dm + o_progs;
+    A.seg_len = (const uint64_t*)(dm + o_seglen);
+    A.seg_out = (uint64_t*)(dm + o_segout);
+    A.in = dev_io ? (const uint8_t*)nullptr : (const uint8_t*)ctx->d_in.p;
+    A.out = dev_io ? (uint8_t*)nullptr : (uint8_t*)ctx->d_out.p;
+    A.arena = (uint8_t*)ctx->ws;
+    A.status = (int32_t*)(dm + o_status);
+    A.out_len = (uint64_t*)(dm + o_outlen);
+    A.counter = (unsigned int*)(dm + o_counter);
+    A.tables = ctx->d_tables;
+    A.nblk = nb;
+
+    CK(cudaEventRecord(ev[1], st), "event");
+    CK(zpq_launch_init(&A, nb, st), "zpq_init_kernel launch");
+    CK(cudaEventRecord(ev[2], st), "event");
+    CK(zpq_launch_code(&A, nb, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
+    CK(cudaEventRecord(ev[3], st), "event");
+    ctx->launches += 2;
+
+    std::vector<int32_t> status(nb);
+    std::vector<uint64_t> out_len(nb), seg_out(nseg);
+    CK(cudaMemcpyAsync(status.data(), dm + o_status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st), "D2H status");
+    CK(cudaMemcpyAsync(out_len.data(), dm + o_outlen, (size_t)nb * 8, cudaMemcpyDeviceToHost, st), "D2H lengths");
+    CK(cudaMemcpyAsync(seg_out.data(), dm + o_segout, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st), "D2H segments");
+    CK(cudaStreamSynchronize(st), "zpq_code_kernel");
+    for (int k = 0; k < nb; ++k) {
+      IJob& J = jobs[wave[k]];
+      J.status = status[k];
+      J.out_len = out_len[k];
+      for (uint32_t s = 0; s < blocks[k].nseg; ++s) J.seg_out[s] = seg_out[blocks[k].seg_first + s];
+    }
+    if (!dev_io) {
+      // first decoded byte of each block (the post-processor flag) + payload copies
+      for (int k = 0; k < nb; ++k) {
+        IJob& J = jobs[wave[k]];
+        if (J.status != ZPQ_OK && J.status != ZPQ_E_OUTPUT_FULL) continue;
+        const uint64_t have = std::min(J.out_len, blocks[k].out_cap);
+        const uint8_t* src = (const uint8_t*)ctx->d_out.p + blocks[k].out_off;
+        if (J.out_skip && have) {
+          uint8_t fb = 0;
+          CK(cudaMemcpyAsync(&fb, src, 1, cudaMemcpyDeviceToHost, st), "D2H flag");
+          CK(cudaStreamSynchronize(st), "sync");
+          J.first_byte = fb;
+        }
+        if (have > J.out_skip && J.out)
+          CK(cudaMemcpyAsync(J.out, src + J.out_skip, have - J.out_skip, cudaMemcpyDeviceToHost, st), "D2H output");
+      }
+    }
+    CK(cudaStreamSynchronize(st), "stream sync");
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ev[1], ev[2]);
+    cudaEventElapsedTime(&b, ev[2], ev[3]);
+    ms_init += a; ms_code += b;
+  }
+  ms_all = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  ctx->ms[0] = ms_init; ctx->ms[1] = ms_code; ctx->ms[2] = ms_all;
+  return ZPQ_OK;
+}
+
+int jobs_from_abi(int nblk, zpq_job* jobs, std::vector<IJob>* out) {
+  if (nblk < 0 || (nblk > 0 && !jobs)) return ZPQ_E_ARG;
+  out->resize(nblk);
+  for (int i = 0; i < nblk; ++i) {
+    IJob& J = (*out)[i];
+    J.hdr = jobs[i].hdr; J.hlen = jobs[i].hlen;
+    J.in.push_back(Piece{jobs[i].data, jobs[i].len});
+    if (jobs[i].seg_len && jobs[i].nseg > 0) J.seg_len.assign(jobs[i].seg_len, jobs[i].seg_len + jobs[i].nseg);
+    else J.seg_len.assign(1, jobs[i].len);
+    J.out = jobs[i].out; J.out_cap = jobs[i].out_cap;
+  }
+  return ZPQ_OK;
+}
+
+void jobs_to_abi(const std::vector<IJob>& in, zpq_job* jobs) {
+  for (size_t i = 0; i < in.size(); ++i) {
+    jobs[i].status = in[i].status;
+    jobs[i].out_len = in[i].out_len;
+    if (jobs[i].seg_out) for (size_t s = 0; s < in[i].seg_out.size(); ++s) jobs[i].seg_out[s] = in[i].seg_out[s];
+  }
+}
+
+int abi_batch(zpq_ctx* ctx, int nblk, zpq_job* jobs, bool decode, bool dev_io) {
+  if (!ctx) return ZPQ_E_ARG;
+  std::vector<IJob> ij;
+  int rc = jobs_from_abi(nblk, jobs, &ij);
+  if (rc != ZPQ_OK) return rc;
+  rc = run_batch(ctx, ij, decode, dev_io);
+  jobs_to_abi(ij, jobs);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zpq_abi_version(void) { return ZPQ_ABI_VERSION; }
+
+const char* zpq_strerror(int s) {
+  switch (s) {
+    case ZPQ_OK: return "ok";
+    case ZPQ_E_HEADER: return "invalid block header";
+    case ZPQ_E_COMPONENT: return "invalid component";
+    case ZPQ_E_VM: return "ZPAQL execution error";
+    case ZPQ_E_OUTPUT_FULL: return "output buffer too small";
+    case ZPQ_E_CORRUPT: return "archive corrupted";
+    case ZPQ_E_EOF: return "unexpected end of file";
+    case ZPQ_E_NOMEM: return "Out of memory";
+    case ZPQ_E_UNSUPPORTED: return "not supported by the B200 context-mixing core";
+    case ZPQ_E_CUDA: return "CUDA error";
+    case ZPQ_E_ARG: return "bad argument";
+    case ZPQ_E_EOS: return "decoding end of stream";
+    case ZPQ_E_CHECKSUM: return "checksum mismatch";
+    case ZPQ_E_METHOD: return "Unsupported method";
+    default: return "unknown status";
+  }
+}
+
+int zpq_create(int device, zpq_ctx** out) {
+  if (!out) return ZPQ_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return ZPQ_E_CUDA; }
+  zpq_ctx* ctx = new zpq_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
+  for (int i = 0; i < 4; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
+  ZTables* T = new ZTables();
+  build_tables(T);
+  e = cudaMalloc((void**)&ctx->d_tables, sizeof(ZTables));
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, T, sizeof(ZTables), cudaMemcpyHostToDevice);
+  delete T;
+  if (e != cudaSuccess) { cudaGetLastError(); zpq_destroy(ctx); return ZPQ_E_CUDA; }
+  *out = ctx;
+  return ZPQ_OK;
+}
+
+void zpq_destroy(zpq_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release();
+  if (ctx->own_ws && ctx->ws) cudaFree(ctx->ws);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* zpq_last_error(const zpq_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int zpq_set_workspace(zpq_ctx* ctx, void* p, uint64_t bytes) {
+  if (!ctx) return ZPQ_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_ws && ctx->ws) cudaFree(ctx->ws);
+  ctx->ws = p; ctx->ws_bytes = p ? bytes : 0; ctx->own_ws = (p == nullptr);
+  if (!p) { ctx->ws = nullptr; ctx->ws_bytes = 0; }
+  return ZPQ_OK;
+}
+
+int zpq_set_stream(zpq_ctx* ctx, void* stream) {
+  if (!ctx) return ZPQ_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); ctx->stream = nullptr; }
+  if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return ZPQ_E_CUDA;
+    ctx->own_stream = true;
+  }
+  return ZPQ_OK;
+}
+
+int zpq_model_bytes(const uint8_t* hdr, int hlen, uint64_t* bytes) {
+  ZModel M; std::vector<uint8_t> img; std::string e;
+  const int rc = compile_model(hdr, hlen, &M, &img, &e);
+  if (rc == ZPQ_OK && bytes) *bytes = M.arena_bytes;
+  return rc;
+}
+
+int zpq_model_from_method(const char* method, const uint8_t* data, uint64_t n, uint8_t* hdr, int cap, int* hlen) {
+  if (!method || !hdr || !hlen) return ZPQ_E_ARG;
+  std::vector<uint8_t> h; std::string e;
+  const int rc = header_from_method(method, data, n, &h, &e);
+  if (rc != ZPQ_OK) return rc;
+  if ((int)h.size() > cap) return ZPQ_E_OUTPUT_FULL;
+  memcpy(hdr, h.data(), h.size());
+  *hlen = (int)h.size();
+  return ZPQ_OK;
+}
+
+int zpq_encode_blocks(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, false, false); }
+int zpq_decode_blocks(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, true, false); }
+int zpq_encode_blocks_dev(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, false, true); }
+int zpq_decode_blocks_dev(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, true, true); }
+
+int zpq_last_timing(const zpq_ctx* ctx, float ms[3]) {
+  if (!ctx || !ms) return ZPQ_E_ARG;
+  ms[0] = ctx->ms[0]; ms[1] = ctx->ms[1]; ms[2] = ctx->ms[2];
+  return ZPQ_OK;
+}
+
+uint64_t zpq_launch_count(const zpq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t zpq_compress_bound(uint64_t len) { return len + len / 8 + 1024; }
+
+// Batched libzpaq::compressBlock (libzpaq.cpp:7543-7731), context-model family only.
+int zpq_compress_blocks(zpq_ctx* ctx, int nblk, const char* method, const uint8_t* const* data,
+                        const uint64_t* len, const char* const* filenames, const char* const* comments,
+                        int dosha1, uint8_t* const* out, const uint64_t* out_cap, uint64_t* out_len,
+                        int32_t* status) {
+  if (!ctx || nblk < 0 || !method || (nblk && (!data || !len || !out || !out_cap || !out_len))) return ZPQ_E_ARG;
+  static const uint8_t kPass = 0;   // post-processor flag PASS goes through the model first (libzpaq.cpp:2914)
+  std::vector<std::vector<uint8_t>> hdrs(nblk), pro(nblk);
+  std::vector<std::vector<uint8_t>> sha(nblk);
+  std::vector<int> st(nblk, ZPQ_OK);
+  // host-side per-block work (model selection incl. the level-5 scan, SHA-1) on all host threads
+  {
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    nt = std::min<unsigned>(nt, (unsigned)std::max(1, nblk));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        for (int i = (int)t; i < nblk; i += (int)nt) {
+          std::string e;
+          if (len[i] > 0x7fffffffull - 4096) { st[i] = ZPQ_E_ARG; continue; }
+          st[i] = header_from_method(method, data[i], len[i], &hdrs[i], &e);
+          if (st[i] != ZPQ_OK) continue;
+          char cs[32];
+          snprintf(cs, sizeof(cs), "%llu", (unsigned long long)len[i]);
+          std::string comment = cs;                                   // libzpaq.cpp:7702-7703
+          if (comments && comments[i]) { comment += " "; comment += comments[i]; }
+          write_block_prologue(&pro[i], hdrs[i].data(), (int)hdrs[i].size(),
+                               filenames ? filenames[i] : nullptr, comment.c_str());
+          if (dosha1) { sha[i].resize(20); sha1_of(data[i], len[i], sha[i].data()); }
+        }
+      });
+    for (auto& t : th) t.join();
+  }
+  std::vector<IJob> jobs;
+  std::vector<int> idx;
+  for (int i = 0; i < nblk; ++i) {
+    if (st[i] != ZPQ_OK) continue;
+    const uint64_t tail = 4 + (dosha1 ? 21 : 1) + 1;
+    if (out_cap[i] < pro[i].size() + tail + 8) { st[i] = ZPQ_E_OUTPUT_FULL; continue; }
+    IJob J;
+    J.hdr = hdrs[i].data(); J.hlen = (int)hdrs[i].size();
+    J.in.push_back(Piece{&kPass, 1});
+    J.in.push_back(Piece{data[i], len[i]});
+    J.seg_len.assign(1, len[i] + 1);
+    J.out = out[i] + pro[i].size();
+    J.out_cap = out_cap[i] - pro[i].size() - tail;
+    jobs.push_back(J); idx.push_back(i);
+  }
+  int rc = run_batch(ctx, jobs, false, false);
+  for (size_t k = 0; k < jobs.size(); ++k) {
+    const int i = idx[k];
+    st[i] = jobs[k].status;
+    if (st[i] != ZPQ_OK) continue;
+    memcpy(out[i], pro[i].data(), pro[i].size());
+    uint8_t* p = out[i] + pro[i].size() + jobs[k].out_len;
+    p[0] = p[1] = p[2] = p[3] = 0;                       // Compressor::endSegment, libzpaq.cpp:2956-2966
+    p += 4;
+    if (dosha1) { *p++ = 253; memcpy(p, sha[i].data(), 20); p += 20; }
+    else *p++ = 254;
+    *p++ = 255;                                          // Compressor::endBlock, libzpaq.cpp:3002
+    out_len[i] = (uint64_t)(p - out[i]);
+  }
+  int first_bad = ZPQ_OK;
+  for (int i = 0; i < nblk; ++i) {
+    if (status) status[i] = st[i];
+    if (st[i] != ZPQ_OK && first_bad == ZPQ_OK) first_bad = st[i];
+  }
+  return rc != ZPQ_OK ? rc : first_bad;
+}
+
+// Batched libzpaq::decompress (libzpaq.cpp:2376-2389) over an in-memory archive.
+// The block framing does not store decoded sizes.  compressBlock writes the
+// size as the decimal prefix of the segment comment (libzpaq.cpp:7702), so
+// when every segment carries one the payloads are decoded straight into
+// their final positions; otherwise blocks go through host staging buffers
+// whose capacity grows until the decode fits.
+static int64_t comment_size_hint(const uint8_t* arc, const SegmentView& s) {
+  if (s.comment_len == 0 || s.comment_len > 40) return -1;
+  uint64_t v = 0; uint64_t k = 0;
+  const uint8_t* c = arc + s.comment_off;
+  while (k < s.comment_len && c[k] >= '0' && c[k] <= '9' && k < 12) v = v * 10 + (c[k++] - '0');
+  if (k == 0 || (k < s.comment_len && c[k] != ' ')) return -1;
+  return (int64_t)v;
+}
+
+int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, uint8_t* out, uint64_t out_cap,
+                           uint64_t* out_len, int* nblocks, int verify_sha1) {
+  if (!ctx || !arc || !out_len) return ZPQ_E_ARG;
+  *out_len = 0;
+  std::vector<BlockView> bv; std::string e;
+  int rc = scan_archive(arc, arc_len, &bv, &e);
+  if (rc != ZPQ_OK) { ctx->err = e; return rc; }
+  if (nblocks) *nblocks = (int)bv.size();
+  const size_t nb = bv.size();
+  if (nb == 0) return ZPQ_OK;
+
+  std::vector<IJob> jobs(nb);
+  std::vector<int64_t> hint(nb, 0);
+  bool all_hinted = true;
+  for (size_t i = 0; i < nb; ++i) {
+    IJob& J = jobs[i];
+    J.hdr = arc + bv[i].hdr_off; J.hlen = bv[i].hlen;
+    for (const SegmentView& s : bv[i].segs) {
+      J.in.push_back(Piece{arc + s.coded_off, s.coded_len});
+      J.seg_len.push_back(s.coded_len);
+      const int64_t h = comment_size_hint(arc, s);
+      if (h < 0 || hint[i] < 0) hint[i] = -1; else hint[i] += h;
+    }
+    if (bv[i].segs.empty()) hint[i] = -1;
+    if (hint[i] < 0) all_hinted = false;
+  }
+  int first_bad = ZPQ_OK;
+  auto note = [&](int code) { if (code != ZPQ_OK && first_bad == ZPQ_OK) first_bad = code; };
+
+  std::vector<std::vector<uint8_t>> tmp;
+  std::vector<uint64_t> pos(nb, 0);
+  bool direct = all_hinted;
+  if (direct) {
+    uint64_t p = 0;
+    for (size_t i = 0; i < nb; ++i) { pos[i] = p; p += (uint64_t)hint[i]; }
+    if (p > out_cap || !out) direct = false;
+  }
+  if (direct) {
+    for (size_t i = 0; i < nb; ++i) {
+      jobs[i].out = out + pos[i]; jobs[i].out_cap = (uint64_t)hint[i]; jobs[i].out_skip = 1;   // drop the PASS flag byte
+    }
+    rc = run_batch(ctx, jobs, true, false);
+    if (rc != ZPQ_OK) return rc;
+    for (size_t i = 0; i < nb && direct; ++i)
+      if (jobs[i].status == ZPQ_E_OUTPUT_FULL || (jobs[i].status == ZPQ_OK && jobs[i].out_len != (uint64_t)hint[i] + 1))
+        direct = false;     // a comment lied about the size: redo through staging
+  }
+  if (!direct) {
+    tmp.resize(nb);
+    std::vector<size_t> pending(nb);
+    for (size_t i = 0; i < nb; ++i) pending[i] = i;
+    std::vector<uint64_t> cap(nb);
+    for (size_t i = 0; i < nb; ++i) cap[i] = hint[i] >= 0 ? (uint64_t)hint[i] + 1 : (uint64_t)4 << 20;
+    while (!pending.empty()) {
+      std::vector<IJob> sub;
+      for (size_t i : pending) {
+        tmp[i].resize(cap[i]);
+        IJob J = jobs[i];
+        J.out = tmp[i].data(); J.out_cap = cap[i]; J.out_skip = 0;
+        sub.push_back(J);
+      }
+      rc = run_batch(ctx, sub, true, false);
+      if (rc != ZPQ_OK) return rc;
+      std::vector<size_t> again;
+      for (size_t k = 0; k < pending.size(); ++k) {
+        const size_t i = pending[k];
+        jobs[i].status = sub[k].status; jobs[i].out_len = sub[k].out_len; jobs[i].seg_out = sub[k].seg_out;
+        jobs[i].first_byte = tmp[i].empty() ? -1 : tmp[i][0];
+        if (sub[k].status == ZPQ_E_OUTPUT_FULL && cap[i] < ((uint64_t)1 << 31)) {
+          cap[i] = std::min<uint64_t>(std::max(cap[i] * 8, sub[k].out_len), (uint64_t)1 << 31);
+          again.push_back(i);
+        }
+      }
+      pending.swap(again);
+    }
+    uint64_t p = 0;
+    for (size_t i = 0; i < nb; ++i) {
+      pos[i] = p;
+      if (jobs[i].status != ZPQ_OK || jobs[i].out_len < 1) continue;
+      const uint64_t n = jobs[i].out_len - 1;
+      if (p + n <= out_cap && out) memcpy(out + p, tmp[i].data() + 1, n);
+      else note(ZPQ_E_OUTPUT_FULL);
+      p += n;
+    }
+  }
+  // per-block checks: status, post-processor flag, stored checksums
+  std::vector<int> st(nb, ZPQ_OK);
+  {
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    nt = std::min<unsigned>(nt, (unsigned)nb);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        for (size_t i = t; i < nb; i += nt) {
+          const IJob& J = jobs[i];
+          if (J.status != ZPQ_OK) { st[i] = J.status; continue; }
+          if (J.out_len < 1) { st[i] = ZPQ_E_CORRUPT; continue; }
+          if (J.first_byte != 0) { st[i] = ZPQ_E_UNSUPPORTED; continue; }   // PROG: PCOMP post-processing, outside this path
+          if (!verify_sha1 || pos[i] + J.out_len - 1 > out_cap || !out) continue;
+          uint64_t at = pos[i];
+          for (size_t s = 0; s < J.seg_out.size(); ++s) {
+            const uint64_t n = J.seg_out[s] - (s == 0 ? 1 : 0);
+            if (bv[i].segs[s].has_sha1) {
+              uint8_t d[20];
+              sha1_of(out + at, n, d);
+              if (memcmp(d, bv[i].segs[s].sha1, 20) != 0) st[i] = ZPQ_E_CHECKSUM;
+            }
+            at += n;
+          }
+        }
+      });
+    for (auto& t : th) t.join();
+  }
+  uint64_t total = 0;
+  for (size_t i = 0; i < nb; ++i) {
+    note(st[i]);
+    if (st[i] == ZPQ_OK || st[i] == ZPQ_E_CHECKSUM) total = pos[i] + jobs[i].out_len - 1;
+  }
+  if (first_bad == ZPQ_E_UNSUPPORTED) ctx->err = "PCOMP post-processing is outside the context-mixing path";
+  *out_len = total;
+  return first_bad;
+}
+
+}  // extern "C"

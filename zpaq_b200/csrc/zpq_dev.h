@@ -1,0 +1,107 @@
+// zpq_dev.h -- structures shared by the host model compiler (zpq_model.cpp), the
+// C-ABI layer (zpq_abi.cu) and the kernels (zpq_kernels.cu).
+//
+// HBM layout
+//   workspace = [ block 0 arena | block 1 arena | ... ]     (arena_off, 256-byte aligned)
+//   one arena = every table of one block's model, each table 128-byte aligned:
+//       per component: cm (u32) / a16 (u16) / ht (u8) tables sized as
+//       Predictor::init allocates them (libzpaq.cpp:1768-1850),
+//       then the HCOMP machine: M (2^hm bytes), H (2^hh u32), R (256 u32)
+//       (ZPAQL::init, libzpaq.cpp:1009-1024).
+//   A block's tables are touched by exactly one warp, so they need no
+//   coherence beyond program order.
+#ifndef ZPQ_DEV_H
+#define ZPQ_DEV_H
+#include <stdint.h>
+
+enum { ZT_NONE = 0, ZT_CONS, ZT_CM, ZT_ICM, ZT_MATCH, ZT_AVG, ZT_MIX2, ZT_MIX, ZT_ISSE, ZT_SSE };
+
+#define ZPQ_MAX_LANES 32      // components per model on the warp-per-block path
+#define ZPQ_MAX_STEPS 32
+#define ZPQ_GUARD_LO 128      // zero guard before the HCOMP program (libzpaq.cpp:913)
+#define ZPQ_GUARD_HI 132      // zero guard after it (operand fetches past a +128 jump)
+#define ZPQ_STEP_PAR 0xff
+
+// One component as the kernel sees it (32 bytes).
+struct ZComp {
+  uint8_t type, a1, a2, a3, a4, a5;  // type byte and arguments as in the header
+  uint8_t step;                      // index+1 of the step that produces p[i]; 0 = phase A
+  uint8_t sizebits;                  // a1 copy (kept for clarity in find())
+  uint32_t cm_off16;                 // cm / a16 table offset in the arena, 16-byte units
+  uint32_t ht_off16;                 // ht table offset, 16-byte units
+  uint32_t cm_mask;                  // entries-1 of the table indexed through cm(i) / size-1 for MIX, MIX2
+  uint32_t ht_mask;                  // MATCH: buf bytes-1; ICM/ISSE: ht bytes-16
+  uint32_t limit;                    // CM/SSE count limit (arg*4)
+  uint32_t pad;
+};
+
+// One step of the dependent part of predict().
+struct ZStep {
+  uint8_t kind;     // ZPQ_STEP_PAR, or the index of the MIX component computed cooperatively
+  uint8_t m;        // MIX: number of inputs
+  uint8_t j0;       // MIX: first input
+  uint8_t rate;     // MIX: learning rate
+  uint32_t cm_off16;
+};
+
+// Arena initialisation op (zpq_init_kernel).
+enum { ZF_ZERO = 0, ZF_CONST32, ZF_SSE, ZF_ICM, ZF_ISSE, ZF_BYTE1 };
+struct ZFill {
+  uint32_t off16;    // destination offset in the arena, 16-byte units
+  uint32_t n16;      // length in 16-byte units
+  uint32_t kind;
+  uint32_t value;    // ZF_CONST32: word; ZF_SSE: start (low 10 bits)
+};
+#define ZPQ_MAX_FILLS 80
+
+struct ZModel {
+  uint32_t n, hh, hm;
+  uint32_t prog_off;      // offset of the guarded program image in the program pool
+  uint32_t prog_len;      // HCOMP bytes (incl. END) without guards
+  uint32_t nsteps, nfills;
+  uint32_t m_off16, h_off16, r_off16;
+  uint32_t m_mask, h_mask;
+  uint64_t arena_bytes;   // multiple of 256
+  ZComp comp[ZPQ_MAX_LANES];
+  ZStep steps[ZPQ_MAX_STEPS];
+  ZFill fills[ZPQ_MAX_FILLS];
+};
+
+struct ZBlock {
+  uint32_t model;
+  uint32_t seg_first, nseg;
+  uint32_t pad;
+  uint64_t arena_off;
+  uint64_t in_off;        // into the batch input buffer
+  uint64_t out_off, out_cap;
+};
+
+// Model-independent tables (device copies live in the context; the coding
+// kernel stages them in shared memory).
+struct ZTables {
+  int16_t stretch_hi[16384];   // stretcht[16384..32767]; lower half by antisymmetry
+  uint16_t squash[4096];
+  int32_t dt[1024];
+  uint32_t ns[256];            // per state: next0 | next1<<8 | n0<<16 | n1<<24
+  uint16_t dt2k[256];
+  uint32_t icm_init[256];      // st.cminit(j)
+  uint32_t isse_init[512];     // {1<<15, clamp512k(stretch(cminit(j)>>8)*1024)}
+};
+
+struct ZKernelArgs {
+  const ZModel* models;
+  const ZBlock* blocks;
+  const uint8_t* progs;
+  const uint64_t* seg_len;
+  uint64_t* seg_out;
+  const uint8_t* in;
+  uint8_t* out;
+  uint8_t* arena;
+  int32_t* status;
+  uint64_t* out_len;
+  unsigned int* counter;
+  const ZTables* tables;
+  int nblk;
+};
+
+#endif

@@ -1,0 +1,51 @@
+// zpq_host.h -- internal host-side declarations shared by the C-ABI layer, the
+// model compiler, the method->header generator and the framing code.
+#ifndef ZPQ_HOST_H
+#define ZPQ_HOST_H
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/zpq.h"
+#include "zpq_dev.h"
+
+namespace zpq {
+
+// zpq_model.cpp
+void build_state_table(uint8_t ns[1024]);
+void build_tables(ZTables* T);
+int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>* image, std::string* err);
+
+// zpq_method.cpp : method string (+ payload statistics) -> block header bytes
+int header_from_method(const char* method, const uint8_t* data, uint64_t n,
+                       std::vector<uint8_t>* hdr, std::string* err);
+
+// zpq_frame.cpp : SHA-1 and block framing
+struct Sha1 {
+  uint32_t h[5]; uint64_t len; uint8_t buf[64]; int fill;
+  Sha1() { reset(); }
+  void reset();
+  void update(const uint8_t* p, uint64_t n);
+  void finish(uint8_t out[20]);
+};
+void sha1_of(const uint8_t* p, uint64_t n, uint8_t out[20]);
+
+struct SegmentView {            // one segment located inside an archive
+  uint64_t coded_off, coded_len;   // coded bytes INCLUDING the 4-zero terminator
+  uint64_t comment_off, comment_len;
+  bool has_sha1; uint8_t sha1[20];
+};
+struct BlockView {
+  uint64_t hdr_off; int hlen;      // header bytes hsize[2]..HCOMP END
+  int level;
+  std::vector<SegmentView> segs;
+  uint64_t end;                    // offset one past the 255 end-of-block byte
+};
+// Decompresser::findBlock/findFilename/readComment/readSegmentEnd (libzpaq.cpp:2247-2373) over memory
+int scan_archive(const uint8_t* arc, uint64_t n, std::vector<BlockView>* blocks, std::string* err);
+// Compressor::writeTag/startBlock/startSegment (libzpaq.cpp:2776-2883): bytes before the coded data
+void write_block_prologue(std::vector<uint8_t>* out, const uint8_t* hdr, int hlen,
+                          const char* filename, const char* comment);
+
+}  // namespace zpq
+#endif
