@@ -102,6 +102,11 @@ int zpq_model_bytes(const uint8_t* hdr, int hlen, uint64_t* bytes);
  * The payload is needed because level 5 analyses it (libzpaq.cpp:7655-7688). */
 int zpq_model_from_method(const char* method, const uint8_t* data, uint64_t n,
                           uint8_t* hdr, int cap, int* hlen);
+/* Diagnostics of the kernel plan for a header: info[0]=components, [1]=predict steps,
+ * [2]=shared-memory bytes per block, [3]=1 if HCOMP runs as lane-parallel recipes
+ * (0: bytecode interpreter), [4]=recipe rounds, [5]=ICM/ISSE tables left in HBM,
+ * [6]=generic-kernel steps, [7]=HCOMP bytes. */
+int zpq_model_describe(const uint8_t* hdr, int hlen, uint32_t info[8]);
 
 /* ---- the hot path -------------------------------------------------------- */
 /* Host buffers in, host buffers out (copies inside).  Replaces the loop

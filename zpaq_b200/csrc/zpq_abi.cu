@@ -6,6 +6,7 @@
 // ZPQ_E_CUDA when no device is usable.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <chrono>
 #include <string.h>
 #include <map>
@@ -63,6 +64,7 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   uint64_t launches = 0;
+  int kernel_version = 2;      // ZPQ_KERNEL=1 selects the generic v1 kernel (A/B testing)
 };
 
 namespace {
@@ -239,7 +241,16 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     CK(cudaEventRecord(ev[1], st), "event");
     CK(zpq_launch_init(&A, nb, st), "zpq_init_kernel launch");
     CK(cudaEventRecord(ev[2], st), "event");
-    CK(zpq_launch_code(&A, nb, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
+    {
+      // v2 kernel: one CTA per SM; W warps share the 227 KB carve-out (static tables + W private regions)
+      uint32_t pw = 16;
+      for (int k = 0; k < nb; ++k) pw = std::max(pw, models[jobs[wave[k]].model].pw_bytes);
+      int warps = (int)std::min<uint64_t>(8, (ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem()) / pw);
+      if (ctx->kernel_version == 1 || warps < 1)
+        CK(zpq_launch_code(&A, nb, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
+      else
+        CK(zpq_launch_code2(&A, nb, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
+    }
     CK(cudaEventRecord(ev[3], st), "event");
     ctx->launches += 2;
 
@@ -349,6 +360,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return ZPQ_E_CUDA; }
   zpq_ctx* ctx = new zpq_ctx();
   ctx->device = device;
+  if (const char* kv = getenv("ZPQ_KERNEL")) ctx->kernel_version = atoi(kv) == 1 ? 1 : 2;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -403,6 +415,22 @@ int zpq_model_bytes(const uint8_t* hdr, int hlen, uint64_t* bytes) {
   ZModel M; std::vector<uint8_t> img; std::string e;
   const int rc = compile_model(hdr, hlen, &M, &img, &e);
   if (rc == ZPQ_OK && bytes) *bytes = M.arena_bytes;
+  return rc;
+}
+
+// Diagnostics: info[0]=n, [1]=v2 steps, [2]=per-warp shared bytes, [3]=recipes ok, [4]=recipe rounds,
+// [5]=components whose ICM/ISSE table stays in HBM, [6]=v1 steps, [7]=HCOMP bytes
+int zpq_model_describe(const uint8_t* hdr, int hlen, uint32_t info[8]) {
+  ZModel* M = new ZModel(); std::vector<uint8_t> img; std::string e;
+  const int rc = compile_model(hdr, hlen, M, &img, &e);
+  if (rc == ZPQ_OK && info) {
+    info[0] = M->n; info[1] = M->nsteps2; info[2] = M->pw_bytes; info[3] = M->rcp.ok; info[4] = M->rcp.nrounds;
+    uint32_t spilled = 0;
+    for (uint32_t i = 0; i < M->n; ++i)
+      if ((M->comp[i].type == ZT_ICM || M->comp[i].type == ZT_ISSE) && M->smem_off[i] == 0xffffffffu) ++spilled;
+    info[5] = spilled; info[6] = M->nsteps; info[7] = M->prog_len;
+  }
+  delete M;
   return rc;
 }
 

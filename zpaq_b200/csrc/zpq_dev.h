@@ -21,6 +21,8 @@ enum { ZT_NONE = 0, ZT_CONS, ZT_CM, ZT_ICM, ZT_MATCH, ZT_AVG, ZT_MIX2, ZT_MIX, Z
 #define ZPQ_GUARD_LO 128      // zero guard before the HCOMP program (libzpaq.cpp:913)
 #define ZPQ_GUARD_HI 132      // zero guard after it (operand fetches past a +128 jump)
 #define ZPQ_STEP_PAR 0xff
+// v2 step kinds (ZStep.kind): one uniform branch per step
+enum { ZK_ISSE = 1, ZK_MIX, ZK_MIX2, ZK_SSE, ZK_AVG };
 
 // One component as the kernel sees it (32 bytes).
 struct ZComp {
@@ -44,6 +46,19 @@ struct ZStep {
   uint32_t cm_off16;
 };
 
+// v2: one step = one uniform branch (16 bytes).
+struct alignas(16) ZStep2 {
+  uint8_t kind;     // ZK_*
+  uint8_t owner;    // lane that receives the result (all kinds but ZK_ISSE)
+  uint8_t j, k;     // input lanes: MIX2 j,k; SSE j; AVG j,k; MIX: j = first input, k = number of inputs
+  uint8_t rate;     // MIX learning rate
+  uint8_t q;        // MIX: slot in the per-lane weight registers (0xff: none, reload from memory)
+  uint8_t wt;       // AVG weight
+  uint8_t level;    // ZK_ISSE: lanes whose ZComp.step equals this value compute in this step
+  uint32_t cm_off16;// MIX weight table
+  uint32_t pad;
+};
+
 // Arena initialisation op (zpq_init_kernel).
 enum { ZF_ZERO = 0, ZF_CONST32, ZF_SSE, ZF_ICM, ZF_ISSE, ZF_BYTE1 };
 struct ZFill {
@@ -53,6 +68,27 @@ struct ZFill {
   uint32_t value;    // ZF_CONST32: word; ZF_SSE: start (low 10 bits)
 };
 #define ZPQ_MAX_FILLS 80
+
+// Lane-parallel HCOMP "recipes" (zpq_hcomp.cpp): for programs of the makeConfig
+// family every H[i] is a short fold over recent bytes, so lane i evaluates its
+// own hash natively instead of the warp interpreting the bytecode.
+#define ZPQ_RCP_MAX 16
+enum { ZR_END = 0, ZR_FOLD, ZR_SHL8ADD, ZR_SHR, ZR_SHL, ZR_ROLL, ZR_WORD, ZR_WORD2 };
+enum { ZS_NONE = 0, ZS_BYTE, ZS_POSAND, ZS_POSMOD, ZS_DIST };
+enum { ZB_ZERO = 0, ZB_OWN, ZB_LANE };
+// op word: op | src<<4 | arg<<8 | off<<16
+#define ZR_WORD_OF(op, src, arg, off) ((uint32_t)(op) | (uint32_t)(src) << 4 | (uint32_t)(arg) << 8 | (uint32_t)(off) << 16)
+struct ZRecipes {
+  uint32_t ok;             // 1: recipes reproduce the HCOMP program exactly (host-verified)
+  uint32_t nrounds;
+  uint32_t needs_lastpos;  // some recipe reads the H[255+k] "last position of byte k" slots
+  uint32_t has_word;
+  uint8_t start[32];       // ZB_*
+  uint8_t base[32];        // ZB_LANE: lane whose (new) hash seeds this one
+  uint8_t round[32];
+  uint8_t len[32];
+  uint32_t ops[ZPQ_RCP_MAX][32];
+};
 
 struct ZModel {
   uint32_t n, hh, hm;
@@ -65,6 +101,13 @@ struct ZModel {
   ZComp comp[ZPQ_MAX_LANES];
   ZStep steps[ZPQ_MAX_STEPS];
   ZFill fills[ZPQ_MAX_FILLS];
+  // ---- v2 kernel (zpq_kernels2.cu) ----
+  uint32_t pw_bytes;                    // per-warp shared memory this model wants
+  uint32_t smem_off[ZPQ_MAX_LANES];     // byte offset of the component's cm table in the warp's region, ~0u = stays in HBM
+  uint32_t nsteps2;
+  ZStep2 steps2[ZPQ_MAX_STEPS];         // kind-specialised step list (ZK_*)
+  uint8_t step2[ZPQ_MAX_LANES];          // ISSE lanes: level at which the lane computes
+  ZRecipes rcp;
 };
 
 struct ZBlock {

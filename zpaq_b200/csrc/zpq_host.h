@@ -16,6 +16,9 @@ void build_state_table(uint8_t ns[1024]);
 void build_tables(ZTables* T);
 int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>* image, std::string* err);
 
+// zpq_hcomp.cpp : HCOMP bytecode -> lane-parallel recipes (self-checked)
+void build_recipes(ZModel* M, const uint8_t* prog, int prog_len);
+
 // zpq_method.cpp : method string (+ payload statistics) -> block header bytes
 int header_from_method(const char* method, const uint8_t* data, uint64_t n,
                        std::vector<uint8_t>* hdr, std::string* err);

@@ -4,11 +4,18 @@
 #include <cuda_runtime.h>
 #include "zpq_dev.h"
 
-#define ZPQ_WARPS 4   // warps (= archive blocks in flight) per CTA
+#define ZPQ_WARPS 4   // v1 kernel: warps (= archive blocks in flight) per CTA
+#define ZPQ_SMEM_MAX 232448   // 227 KB: per-CTA dynamic shared memory limit on sm_100
+#define ZPQ_MIXREG_HOST 3     // must equal ZPQ_MIXREG in zpq_kernels2.cu
 
 extern "C" {
 size_t zpq_code_kernel_smem(void);
 cudaError_t zpq_launch_init(const ZKernelArgs* a, int nblk, cudaStream_t st);
 cudaError_t zpq_launch_code(const ZKernelArgs* a, int nblk, int decode, int sm_count, cudaStream_t st);
+// v2 (production) kernel: one CTA per SM, `warps` blocks in flight per CTA,
+// `pw_bytes` of shared memory per warp for the ICM/ISSE tables.
+int zpq_code2_static_smem(void);
+cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int decode, int sm_count, int warps, int pw_bytes,
+                             cudaStream_t st);
 }
 #endif

@@ -1,0 +1,657 @@
+// zpq_kernels2.cu -- the production coding kernel (v2) for sm_100a.
+//
+// Same mapping as zpq_kernels.cu (one warp = one archive block, lane i =
+// component i, coder fused in) but rebuilt around what the v1 ncu profile
+// showed (profiles/r01_v1_*): the loop is bound by issued instructions and by
+// dependent memory round trips, not by bandwidth.  So:
+//   * ICM / ISSE probability and weight tables (1-2 KB each) live in SHARED
+//     memory for the lifetime of the block; only hash rows, CM/SSE/MIX tables
+//     and the MATCH buffers stay in HBM.  One CTA per SM, W = 7 or 8 warps,
+//     the whole 227 KB carve-out used.
+//   * the dependent part of predict() is a list of kind-specialised steps
+//     (one uniform branch each): an ISSE level is 1 shuffle + 5 ALU ops.
+//   * MIX weight rows are fetched once per bit into registers (coalesced, lane
+//     l = weight l), reduced with redux.sync, and written back from the same
+//     registers in update().
+//   * HCOMP: programs of the makeConfig family are evaluated as per-lane
+//     recipes (zpq_hcomp.cpp), ~20 instructions per input byte per lane
+//     instead of ~9000 warp instructions of bytecode interpretation; any other
+//     program still runs through the bytecode interpreter.
+// Reference semantics: see zpq_kernels.cu (same file:line anchors).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "zpq_dev.h"
+#include "zpq_kernels.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define FULL 0xffffffffu
+#define ST_OK 0
+#define ST_VM (-3)
+#define ST_FULL (-4)
+#define ST_CORRUPT (-5)
+#define ST_EOF (-6)
+#define ST_EOS (-11)
+
+// shared-memory layout of the CTA-wide tables
+#define S2_STRETCH 0                       // i16[16384]  stretcht[16384..32767]
+#define S2_SQUASH (S2_STRETCH + 32768)     // u16[1344]   squasht[1376..2719]
+#define S2_DT (S2_SQUASH + 2688)           // u16[1024]   dt[i]/2
+#define S2_NS (S2_DT + 2048)               // u16[256]    next0 | next1<<8
+#define S2_DT2K (S2_NS + 512)              // u16[256]
+#define S2_STATIC (S2_DT2K + 512)          // 38528
+
+struct Tabs {
+  const short* stretch_hi;
+  const u16* squash;
+  const u16* dt;
+  const u16* ns;
+  const u16* dt2k;
+};
+
+__device__ __forceinline__ int t_stretch(const Tabs& S, u32 x) {
+  return x >= 16384u ? (int)S.stretch_hi[x - 16384u] : -(int)S.stretch_hi[16383u - x];
+}
+// squash(x), x in [-2048, 2047]: 0 below -672, 32767 from 672 up (libzpaq.cpp:1739-1741)
+__device__ __forceinline__ int t_squash(const Tabs& S, int x) {
+  const int i = x + 672;
+  const int v = (int)S.squash[min(max(i, 0), 1343)];
+  return i < 0 ? 0 : (i > 1343 ? 32767 : v);
+}
+__device__ __forceinline__ int clamp2k(int x) { return min(max(x, -2048), 2047); }
+__device__ __forceinline__ int clamp512k(int x) { return min(max(x, -(1 << 19)), (1 << 19) - 1); }
+
+__device__ __forceinline__ u32 row_get(const uint4& r, int k) {
+  u32 w = (k & 8) ? ((k & 4) ? r.w : r.z) : ((k & 4) ? r.y : r.x);
+  return (w >> ((k & 3) * 8)) & 255u;
+}
+__device__ __forceinline__ void row_set(uint4& r, int k, u32 v) {
+  const u32 sh = (k & 3) * 8;
+  const u32 keep = ~(255u << sh), val = v << sh;
+  if (k & 8) { if (k & 4) r.w = (r.w & keep) | val; else r.z = (r.z & keep) | val; }
+  else       { if (k & 4) r.y = (r.y & keep) | val; else r.x = (r.x & keep) | val; }
+}
+
+// Predictor::find (libzpaq.cpp:2072-2088)
+__device__ __forceinline__ void d_find(u8* ht, u32 ht_mask, int shift, u32 cxt, uint4& row, u32& off) {
+  const u32 chk = (cxt >> shift) & 255u;
+  const u32 h0 = (cxt * 16u) & ht_mask, h1 = h0 ^ 16u, h2 = h0 ^ 32u;
+  const uint4 r0 = *reinterpret_cast<const uint4*>(ht + h0);
+  const uint4 r1 = *reinterpret_cast<const uint4*>(ht + h1);
+  const uint4 r2 = *reinterpret_cast<const uint4*>(ht + h2);
+  if ((r0.x & 255u) == chk) { row = r0; off = h0; return; }
+  if ((r1.x & 255u) == chk) { row = r1; off = h1; return; }
+  if ((r2.x & 255u) == chk) { row = r2; off = h2; return; }
+  const u32 p0 = (r0.x >> 8) & 255u, p1 = (r1.x >> 8) & 255u, p2 = (r2.x >> 8) & 255u;
+  if (p0 <= p1 && p0 <= p2) off = h0;
+  else if (p1 < p2) off = h1;
+  else off = h2;
+  row = make_uint4(chk, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------
+// HCOMP bytecode interpreter (fallback for programs without recipes); same
+// semantics as vm_run in zpq_kernels.cu.
+struct Vm2 {
+  u32 a, b, c, d, f;
+  u8* m; u32* h; u32* r;
+  u32 mmask, hmask;
+  const u8* code; int len;
+};
+
+__device__ __noinline__ int vm2_run(Vm2& S, u32 input) {
+  u32 a = input, b = S.b, c = S.c, d = S.d, f = S.f;
+  u8* const m = S.m; u32* const h = S.h; u32* const r = S.r;
+  const u32 mmask = S.mmask, hmask = S.hmask;
+  const u8* const code = S.code;
+  int pc = 0, rc = ST_OK;
+  for (int guard = 0;; ++guard) {
+    if (guard >= (1 << 24)) { rc = ST_VM; break; }
+    const u32 op = code[pc++];
+    if (op == 56) break;
+    if (op < 56) {
+      const u32 tgt = op >> 3, act = op & 7;
+      if (act == 7) {
+        const u32 n = code[pc];
+        if (tgt == 0) { a = r[n]; ++pc; }
+        else if (tgt == 1) { b = r[n]; ++pc; }
+        else if (tgt == 2) { c = r[n]; ++pc; }
+        else if (tgt == 3) { d = r[n]; ++pc; }
+        else if (tgt == 4) { if (f) pc += (int)((n + 128) & 255) - 127; else ++pc; }
+        else if (tgt == 5) { if (!f) pc += (int)((n + 128) & 255) - 127; else ++pc; }
+        else { r[n] = a; ++pc; }
+        continue;
+      }
+      if (act > 4 || op == 0) { rc = ST_VM; break; }
+      u32 v;
+      if (tgt == 0) v = a; else if (tgt == 1) v = b; else if (tgt == 2) v = c; else if (tgt == 3) v = d;
+      else if (tgt == 4) v = m[b & mmask]; else if (tgt == 5) v = m[c & mmask]; else v = h[d & hmask];
+      if (act == 0) {
+        const u32 olda = a;
+        if (tgt == 4 || tgt == 5) { a = (olda & 0xffffff00u) | (v & 255u); v = olda & 255u; }
+        else { a = v; v = olda; }
+      }
+      else if (act == 1) ++v;
+      else if (act == 2) --v;
+      else if (act == 3) v = ~v;
+      else v = 0;
+      if (tgt == 0) a = v; else if (tgt == 1) b = v; else if (tgt == 2) c = v; else if (tgt == 3) d = v;
+      else if (tgt == 4) m[b & mmask] = (u8)v; else if (tgt == 5) m[c & mmask] = (u8)v; else h[d & hmask] = v;
+      continue;
+    }
+    if (op < 64) {
+      if (op == 57) continue;
+      if (op == 59) { a = (a + m[b & mmask] + 512u) * 773u; continue; }
+      if (op == 60) { h[d & hmask] = (h[d & hmask] + a + 512u) * 773u; continue; }
+      if (op == 63) { const u32 n = code[pc]; pc += (int)((n + 128) & 255) - 127; continue; }
+      rc = ST_VM; break;
+    }
+    if (op == 255) {
+      const int t = (int)code[pc] + 256 * (int)code[pc + 1];
+      if (t >= S.len) { rc = ST_VM; break; }
+      pc = t; continue;
+    }
+    const u32 grp = op >> 3, src = op & 7;
+    if (grp == 15 || grp >= 30) { rc = ST_VM; break; }
+    u32 v;
+    if (src == 0) v = a; else if (src == 1) v = b; else if (src == 2) v = c; else if (src == 3) v = d;
+    else if (src == 4) v = m[b & mmask]; else if (src == 5) v = m[c & mmask]; else if (src == 6) v = h[d & hmask];
+    else v = code[pc++];
+    switch (grp) {
+      case 8: a = v; break;
+      case 9: b = v; break;
+      case 10: c = v; break;
+      case 11: d = v; break;
+      case 12: m[b & mmask] = (u8)v; break;
+      case 13: m[c & mmask] = (u8)v; break;
+      case 14: h[d & hmask] = v; break;
+      case 16: a += v; break;
+      case 17: a -= v; break;
+      case 18: a *= v; break;
+      case 19: a = v ? a / v : 0u; break;
+      case 20: a = v ? a % v : 0u; break;
+      case 21: a &= v; break;
+      case 22: a &= ~v; break;
+      case 23: a |= v; break;
+      case 24: a ^= v; break;
+      case 25: a <<= (v & 31u); break;
+      case 26: a >>= (v & 31u); break;
+      case 27: f = (a == v); break;
+      case 28: f = (a < v); break;
+      default: f = (a > v); break;
+    }
+  }
+  S.a = a; S.b = b; S.c = c; S.d = d; S.f = f;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// Lane-parallel HCOMP: lane i folds its own op list into h (zpq_hcomp.cpp).
+// `hist` holds the last 8 input bytes (byte 0 = newest); older bytes come from
+// the M ring in HBM, which is still maintained exactly as the program's
+// prologue does (c-- *c=a ... *d=c).
+struct Rcp {
+  const u32* ops;      // [t][lane] in global memory (read-only, L1 resident)
+  u32 start, base, round, len;
+  u32 nrounds, needs_lastpos;
+};
+
+__device__ __forceinline__ u32 hcomp_recipes(const Rcp& R, int lane, u32 h, u32 byte, u32& c, u64& hist,
+                                             u8* m, u32 mmask, u32* H, u32 hmask) {
+  // every lane issues the same stores (same address, same value: one transaction), so each
+  // lane later reads its own writes and no intra-warp fence is needed
+  c -= 1;
+  m[c & mmask] = (u8)byte;
+  if (R.needs_lastpos) H[(byte + 255u) & hmask] = c;
+  hist = (hist << 8) | (u64)byte;
+  const u32 hold_prev = __shfl_up_sync(FULL, h, 1);     // old hash of lane-1 (word-model shift)
+  const u32 hold = h;
+  for (u32 r = 0; r < R.nrounds; ++r) {
+    const u32 hb = __shfl_sync(FULL, h, (int)R.base);
+    if (R.round == r) {
+      u32 acc = R.start == ZB_ZERO ? 0u : (R.start == ZB_OWN ? hold : hb);
+      for (u32 t = 0; t < R.len; ++t) {
+        const u32 w = __ldg(R.ops + t * 32 + lane);
+        const u32 op = w & 15u, src = (w >> 4) & 15u, arg = (w >> 8) & 255u, off = w >> 16;
+        u32 x = 0;
+        if (src == ZS_BYTE) {
+          if (off < 8) x = (u32)(hist >> (off * 8)) & arg;
+          else x = (u32)m[(c + off) & mmask] & arg;
+        }
+        else if (src == ZS_POSAND) x = c & arg;
+        else if (src == ZS_POSMOD) x = arg ? c % arg : 0u;
+        else if (src == ZS_DIST) { x = H[(255u + arg) & hmask] - c; x = min(x, 255u); }
+        if (op == ZR_FOLD) acc = (acc + x + 512u) * 773u;
+        else if (op == ZR_SHL8ADD) acc = (acc << 8) + x;
+        else if (op == ZR_SHR) acc >>= arg;
+        else if (op == ZR_SHL) acc <<= arg;
+        else if (op == ZR_ROLL) acc = acc * off + byte + 1u;
+        else if (op == ZR_WORD) {
+          const u32 w2 = __ldg(R.ops + (t + 1) * 32 + lane);
+          const u32 v2 = off & 255u, v3 = off >> 8, mult = w2 & 255u, first = (w2 >> 8) & 1u;
+          if ((((byte & arg) - v2) & 255u) < v3) acc = acc * mult + byte + 1u;
+          else acc = first ? 0u : hold_prev;
+          ++t;
+        }
+      }
+      h = acc;
+    }
+  }
+  return h;
+}
+
+// ---------------------------------------------------------------------------
+struct Lane2 {
+  u32 type, a1, a2, a3, a4, a5, step;
+  u32* tab;        // cm table: generic pointer (shared memory copy, or HBM)
+  u8* ht;
+  u32 cm_mask, ht_mask, limit;
+  u32 h;
+  int p, xj, xk;
+  u32 cxt, v0, v1, bh;
+  uint4 row; u32 row_off;
+  u32 ma, mb, mpos, mbit, mpred, mc;
+};
+
+struct Coder2 {
+  u32 low, high, curr;
+  const u8* in; u64 in_pos, in_end;
+  u8* out; u64 out_pos, out_cap;
+  int status;
+};
+
+__device__ __forceinline__ void enc_bit(Coder2& C, int lane, int y, u32 p16) {
+  const u32 mid = C.low + (u32)(((u64)(C.high - C.low) * p16) >> 16);
+  if (y) C.high = mid; else C.low = mid + 1;
+  while ((C.high ^ C.low) < 0x1000000u) {
+    if (C.out_pos < C.out_cap) { if (lane == 0) C.out[C.out_pos] = (u8)(C.high >> 24); }
+    else C.status = ST_FULL;
+    ++C.out_pos;
+    C.high = C.high << 8 | 255u;
+    C.low = C.low << 8;
+    C.low += (C.low == 0);
+  }
+}
+
+__device__ __forceinline__ int dec_bit(Coder2& C, u32 p16) {
+  if (C.curr < C.low || C.curr > C.high) { C.status = ST_CORRUPT; return 0; }
+  const u32 mid = C.low + (u32)(((u64)(C.high - C.low) * p16) >> 16);
+  int y;
+  if (C.curr <= mid) { y = 1; C.high = mid; } else { y = 0; C.low = mid + 1; }
+  while ((C.high ^ C.low) < 0x1000000u) {
+    C.high = C.high << 8 | 255u;
+    C.low = C.low << 8;
+    C.low += (C.low == 0);
+    if (C.in_pos >= C.in_end) { C.status = ST_EOF; return y; }
+    C.curr = C.curr << 8 | (u32)C.in[C.in_pos++];
+  }
+  return y;
+}
+
+#define ZPQ_MIXREG 3    // MIX components whose weight row is held in registers across predict/update
+
+struct Mod2 {
+  int n, nsteps;
+  const ZStep2* steps;     // global, read-only
+  u8* arena;
+  int c8, hmap4;
+  int mixw[ZPQ_MIXREG], mixx[ZPQ_MIXREG];
+  u32 mixbase[ZPQ_MIXREG];
+};
+
+__device__ __forceinline__ ZStep2 ld_step(const ZStep2* p) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  ZStep2 s;
+  s.kind = v.x & 255; s.owner = (v.x >> 8) & 255; s.j = (v.x >> 16) & 255; s.k = v.x >> 24;
+  s.rate = v.y & 255; s.q = (v.y >> 8) & 255; s.wt = (v.y >> 16) & 255; s.level = v.y >> 24;
+  s.cm_off16 = v.z; s.pad = v.w;
+  return s;
+}
+
+// Predictor::predict0 (libzpaq.cpp:1854-1951)
+__device__ __forceinline__ int predict2(Lane2& L, Mod2& M, const Tabs& S, int lane) {
+  const int c8 = M.c8, hmap4 = M.hmap4;
+  const bool nib = (c8 == 1) || ((c8 & 0xf0) == 16);
+  if (L.type == ZT_ICM || L.type == ZT_ISSE) {
+    if (nib) d_find(L.ht, L.ht_mask, (int)L.a1 + 2, L.h + 16u * (u32)c8, L.row, L.row_off);
+    L.bh = row_get(L.row, hmap4 & 15);
+    if (L.type == ZT_ISSE) {
+      const uint2 w = *reinterpret_cast<const uint2*>(L.tab + L.bh * 2);
+      L.v0 = w.x; L.v1 = w.y;
+    } else {
+      L.v0 = L.tab[L.bh];
+      L.p = t_stretch(S, L.v0 >> 8);
+    }
+  }
+  else if (L.type == ZT_CM) {
+    L.cxt = (L.h ^ (u32)hmap4) & L.cm_mask;
+    L.v0 = L.tab[L.cxt];
+    L.p = t_stretch(S, L.v0 >> 17);
+  }
+  else if (L.type == ZT_MATCH) {
+    if (L.ma == 0) L.p = 0;
+    else {
+      L.mc = (L.mpred >> (7 - L.mbit)) & 1u;
+      L.p = t_stretch(S, (u32)((int)S.dt2k[L.ma] * (1 - 2 * (int)L.mc)) & 32767u);
+    }
+  }
+  else if (L.type == ZT_MIX2) {
+    L.cxt = (L.h + (u32)(c8 & (int)L.a5)) & L.cm_mask;
+    L.v0 = reinterpret_cast<const u16*>(L.tab)[L.cxt];
+  }
+  else if (L.type == ZT_MIX) L.cxt = ((L.h + (u32)(c8 & (int)L.a5)) & L.cm_mask) * L.a3;
+  else if (L.type == ZT_SSE) L.cxt = (L.h + (u32)c8) * 32u;
+
+  for (int s = 0; s < M.nsteps; ++s) {
+    const ZStep2 st = ld_step(M.steps + s);
+    if (st.kind == ZK_ISSE) {
+      const int pj = __shfl_sync(FULL, L.p, (int)L.a2 & 31);
+      if (L.type == ZT_ISSE && L.step == st.level) {
+        L.xj = pj;
+        L.p = clamp2k(((int)L.v0 * pj + (int)L.v1 * 64) >> 16);
+      }
+    }
+    else if (st.kind == ZK_MIX) {
+      const u32 base = __shfl_sync(FULL, L.cxt, (int)st.owner);
+      const int x = __shfl_sync(FULL, L.p, ((int)st.j + lane) & 31);
+      int w = 0;
+      if (lane < (int)st.k) w = (reinterpret_cast<const int*>(M.arena + (u64)st.cm_off16 * 16))[base + lane];
+      const int sum = __reduce_add_sync(FULL, (w >> 8) * x);
+      if (lane == (int)st.owner) L.p = clamp2k(sum >> 8);
+#pragma unroll
+      for (int q = 0; q < ZPQ_MIXREG; ++q) if (st.q == q) { M.mixw[q] = w; M.mixx[q] = x; M.mixbase[q] = base; }
+    }
+    else if (st.kind == ZK_MIX2) {
+      const int pj = __shfl_sync(FULL, L.p, (int)st.j);
+      const int pk = __shfl_sync(FULL, L.p, (int)st.k);
+      if (lane == (int)st.owner) {
+        L.xj = pj; L.xk = pk;
+        const int w = (int)L.v0;
+        L.p = (w * pj + (65536 - w) * pk) >> 16;
+      }
+    }
+    else if (st.kind == ZK_SSE) {
+      const int pj = __shfl_sync(FULL, L.p, (int)st.j);
+      if (lane == (int)st.owner) {
+        int pq = min(max(pj + 992, 0), 1983);
+        const int wt = pq & 63;
+        pq >>= 6;
+        const u32 c0 = (L.cxt + (u32)pq) & L.cm_mask, c1 = (L.cxt + (u32)pq + 1u) & L.cm_mask;
+        const u32 q0 = L.tab[c0], q1 = L.tab[c1];
+        L.p = t_stretch(S, (u32)(((int)(q0 >> 10) * (64 - wt) + (int)(q1 >> 10) * wt) >> 13));
+        if (wt >> 5) { L.cxt = c1; L.v0 = q1; } else { L.cxt = c0; L.v0 = q0; }
+      }
+    }
+    else {   // ZK_AVG
+      const int pj = __shfl_sync(FULL, L.p, (int)st.j);
+      const int pk = __shfl_sync(FULL, L.p, (int)st.k);
+      if (lane == (int)st.owner) L.p = (pj * (int)st.wt + pk * (256 - (int)st.wt)) >> 8;
+    }
+  }
+  const int pfinal = __shfl_sync(FULL, L.p, M.n - 1);
+  return t_squash(S, pfinal);
+}
+
+// Predictor::update0 component part (libzpaq.cpp:1954-2052)
+__device__ __forceinline__ void update2(Lane2& L, Mod2& M, const Tabs& S, int lane, int y, u32 byte_done) {
+  const int hmap4 = M.hmap4;
+  if (L.type == ZT_ICM || L.type == ZT_ISSE) {
+    const u32 nx = ((u32)S.ns[L.bh] >> (8 * y)) & 255u;
+    row_set(L.row, hmap4 & 15, nx);
+    if (L.type == ZT_ISSE) {
+      const int err = y * 32767 - t_squash(S, L.p);
+      const int w0 = clamp512k((int)L.v0 + ((err * L.xj + (1 << 12)) >> 13));
+      const int w1 = clamp512k((int)L.v1 + ((err + 16) >> 5));
+      *reinterpret_cast<uint2*>(L.tab + L.bh * 2) = make_uint2((u32)w0, (u32)w1);
+    } else {
+      const u32 pn = L.v0;
+      L.tab[L.bh] = pn + (u32)(((int)(y * 32767 - (int)(pn >> 8))) >> 2);
+    }
+  }
+  else if (L.type == ZT_CM || L.type == ZT_SSE) {
+    const u32 pn = L.v0;
+    const u32 count = pn & 0x3ffu;
+    const int err = y * 32767 - (int)(pn >> 17);
+    const u32 prod = (u32)err * ((u32)S.dt[count] * 2u);
+    L.tab[L.cxt] = pn + (prod & 0xfffffc00u) + (count < L.limit ? 1u : 0u);
+  }
+  else if (L.type == ZT_MIX2) {
+    const int err = ((y * 32767 - t_squash(S, L.p)) * (int)L.a4) >> 5;
+    int w = (int)L.v0;
+    w += (err * (L.xj - L.xk) + (1 << 12)) >> 13;
+    w = min(max(w, 0), 65535);
+    reinterpret_cast<u16*>(L.tab)[L.cxt] = (u16)w;
+  }
+  else if (L.type == ZT_MATCH) {
+    if ((int)L.mc != y) L.ma = 0;
+    if (++L.mbit == 8) {
+      L.mbit = 0;
+      L.ht[L.mpos] = (u8)byte_done;
+      L.mpos = (L.mpos + 1) & L.ht_mask;
+      u32* idx = L.tab + (L.h & L.cm_mask);
+      if (L.ma == 0) {
+        L.mb = L.mpos - *idx;
+        if (L.mb & L.ht_mask)
+          while (L.ma < 255 && L.ht[(L.mpos - L.ma - 1) & L.ht_mask] == L.ht[(L.mpos - L.ma - L.mb - 1) & L.ht_mask])
+            ++L.ma;
+      }
+      else L.ma += (L.ma < 255);
+      *idx = L.mpos;
+      L.mpred = L.ht[(L.mpos - L.mb) & L.ht_mask];
+    }
+  }
+  // MIX rows
+  for (int s = 0; s < M.nsteps; ++s) {
+    const ZStep2 st = ld_step(M.steps + s);
+    if (st.kind != ZK_MIX) continue;
+    const int e0 = ((y * 32767 - t_squash(S, L.p)) * (int)st.rate) >> 4;
+    const int err = __shfl_sync(FULL, e0, (int)st.owner);
+    int w = 0, x = 0; u32 base = 0;
+    bool have = false;
+#pragma unroll
+    for (int q = 0; q < ZPQ_MIXREG; ++q) if (st.q == q) { w = M.mixw[q]; x = M.mixx[q]; base = M.mixbase[q]; have = true; }
+    int* wt = reinterpret_cast<int*>(M.arena + (u64)st.cm_off16 * 16);
+    if (!have) {
+      base = __shfl_sync(FULL, L.cxt, (int)st.owner);
+      x = __shfl_sync(FULL, L.p, ((int)st.j + lane) & 31);
+      if (lane < (int)st.k) w = wt[base + lane];
+    }
+    if (lane < (int)st.k) wt[base + lane] = clamp512k(w + ((err * x + (1 << 12)) >> 13));
+  }
+}
+
+// ---------------------------------------------------------------------------
+template <bool DEC>
+__global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, const int pw_bytes) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  {
+    const ZTables* T = A.tables;
+    const uint4* src = reinterpret_cast<const uint4*>(T->stretch_hi);
+    uint4* dst = reinterpret_cast<uint4*>(smem + S2_STRETCH);
+    for (int i = threadIdx.x; i < 32768 / 16; i += blockDim.x) dst[i] = src[i];
+    u16* sq = reinterpret_cast<u16*>(smem + S2_SQUASH);
+    for (int i = threadIdx.x; i < 1344; i += blockDim.x) sq[i] = T->squash[1376 + i];
+    u16* dt = reinterpret_cast<u16*>(smem + S2_DT);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) dt[i] = (u16)(T->dt[i] >> 1);
+    u16* ns = reinterpret_cast<u16*>(smem + S2_NS);
+    u16* d2 = reinterpret_cast<u16*>(smem + S2_DT2K);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { ns[i] = (u16)(T->ns[i] & 0xffffu); d2[i] = T->dt2k[i]; }
+  }
+  __syncthreads();
+  Tabs S;
+  S.stretch_hi = reinterpret_cast<const short*>(smem + S2_STRETCH);
+  S.squash = reinterpret_cast<const u16*>(smem + S2_SQUASH);
+  S.dt = reinterpret_cast<const u16*>(smem + S2_DT);
+  S.ns = reinterpret_cast<const u16*>(smem + S2_NS);
+  S.dt2k = reinterpret_cast<const u16*>(smem + S2_DT2K);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* wsm = smem + S2_STATIC + (size_t)warp * pw_bytes;   // this warp's private region
+
+  for (;;) {
+    int blk = 0;
+    if (lane == 0) blk = (int)atomicAdd(A.counter, 1u);
+    blk = __shfl_sync(FULL, blk, 0);
+    if (blk >= A.nblk) break;
+
+    const ZBlock B = A.blocks[blk];
+    const ZModel* __restrict__ ZM = A.models + B.model;
+    Mod2 M;
+    M.n = (int)ZM->n; M.nsteps = (int)ZM->nsteps2; M.steps = ZM->steps2;
+    M.arena = A.arena + B.arena_off;
+    M.c8 = 1; M.hmap4 = 1;
+#pragma unroll
+    for (int q = 0; q < ZPQ_MIXREG; ++q) { M.mixw[q] = 0; M.mixx[q] = 0; M.mixbase[q] = 0; }
+
+    // ---- lane <-> component ----
+    Lane2 L;
+    {
+      ZComp cd;
+      if (lane < M.n) cd = ZM->comp[lane];
+      else { cd.type = ZT_NONE; cd.a1 = cd.a2 = cd.a3 = cd.a4 = cd.a5 = 0; cd.step = 0; cd.cm_off16 = cd.ht_off16 = 0;
+             cd.cm_mask = cd.ht_mask = cd.limit = 0; }
+      L.type = cd.type; L.a1 = cd.a1; L.a2 = cd.a2; L.a3 = cd.a3; L.a4 = cd.a4; L.a5 = cd.a5;
+      L.step = (lane < M.n) ? ZM->step2[lane] : 0;
+      L.tab = reinterpret_cast<u32*>(M.arena + (u64)cd.cm_off16 * 16);
+      L.ht = M.arena + (u64)cd.ht_off16 * 16;
+      L.cm_mask = cd.cm_mask; L.ht_mask = cd.ht_mask; L.limit = cd.limit;
+      L.h = 0;
+      L.p = (cd.type == ZT_CONS) ? ((int)cd.a1 - 128) * 4 : 0;
+      L.xj = L.xk = 0; L.cxt = 0; L.v0 = L.v1 = 0; L.bh = 0;
+      L.row = make_uint4(0, 0, 0, 0); L.row_off = 0;
+      L.ma = L.mb = L.mpos = L.mbit = L.mc = 0; L.mpred = 0;
+      // ICM / ISSE tables that got a shared-memory slot: initialise it here
+      // (Predictor::init values, libzpaq.cpp:1786-1789, 1829-1833) and use it.
+      const u32 so = (lane < M.n) ? ZM->smem_off[lane] : 0xffffffffu;
+      __syncwarp();
+      for (int src = 0; src < M.n; ++src) {
+        const u32 o = __shfl_sync(FULL, so, src);
+        const u32 ty = __shfl_sync(FULL, L.type, src);
+        if (o == 0xffffffffu) continue;
+        u32* dst = reinterpret_cast<u32*>(wsm + o);
+        if (ty == ZT_ICM) for (int i = lane; i < 256; i += 32) dst[i] = A.tables->icm_init[i];
+        else for (int i = lane; i < 512; i += 32) dst[i] = A.tables->isse_init[i];
+      }
+      if (so != 0xffffffffu) L.tab = reinterpret_cast<u32*>(wsm + so);
+      __syncwarp();
+    }
+
+    // ---- HCOMP ----
+    const bool use_rcp = ZM->rcp.ok != 0;
+    Rcp R;
+    R.ops = &ZM->rcp.ops[0][0];
+    R.start = R.base = R.round = R.len = 0;
+    R.nrounds = ZM->rcp.nrounds; R.needs_lastpos = ZM->rcp.needs_lastpos;
+    if (use_rcp && lane < M.n) { R.start = ZM->rcp.start[lane]; R.base = ZM->rcp.base[lane]; R.round = ZM->rcp.round[lane]; R.len = ZM->rcp.len[lane]; }
+    if (lane >= M.n) R.round = 0xffu;
+    u32 vm_c = 0; u64 hist = 0;
+    Vm2 V;
+    V.a = V.b = V.c = V.d = V.f = 0;
+    V.m = M.arena + (u64)ZM->m_off16 * 16;
+    V.h = reinterpret_cast<u32*>(M.arena + (u64)ZM->h_off16 * 16);
+    V.r = reinterpret_cast<u32*>(M.arena + (u64)ZM->r_off16 * 16);
+    V.mmask = ZM->m_mask; V.hmask = ZM->h_mask;
+    V.len = (int)ZM->prog_len;
+    V.code = A.progs + ZM->prog_off + ZPQ_GUARD_LO;
+
+    Coder2 C;
+    C.low = 1; C.high = 0xffffffffu; C.curr = 0; C.status = ST_OK;
+    C.in = A.in + B.in_off; C.in_pos = 0; C.in_end = 0;
+    C.out = A.out + B.out_off; C.out_pos = 0; C.out_cap = B.out_cap;
+
+    int status = ST_OK;
+    for (u32 sg = 0; sg < B.nseg && status == ST_OK; ++sg) {
+      const u64 seg_n = A.seg_len[B.seg_first + sg];
+      const u64 out_start = C.out_pos;
+      C.in_end = C.in_pos + seg_n;
+      if constexpr (DEC) {
+        C.curr = 0;
+        for (int i = 0; i < 4; ++i) {
+          if (C.in_pos >= C.in_end) { status = ST_EOF; break; }
+          C.curr = C.curr << 8 | (u32)C.in[C.in_pos++];
+        }
+      }
+      for (;;) {
+        if (status != ST_OK) break;
+        int cbyte = 0;
+        if constexpr (!DEC) {
+          if (C.in_pos >= C.in_end) break;
+          cbyte = C.in[C.in_pos++];
+          enc_bit(C, lane, 0, 0);
+        } else {
+          const int eos = dec_bit(C, 0);
+          if (C.status != ST_OK) { status = C.status; break; }
+          if (eos) { if (C.curr != 0) status = ST_EOS; break; }
+        }
+        for (int bit = 7; bit >= 0; --bit) {
+          const u32 p16 = (u32)predict2(L, M, S, lane) * 2u + 1u;
+          int y;
+          if constexpr (!DEC) { y = (cbyte >> bit) & 1; enc_bit(C, lane, y, p16); }
+          else {
+            y = dec_bit(C, p16);
+            if (C.status != ST_OK) { status = C.status; break; }
+          }
+          const int c8n = M.c8 * 2 + y;
+          update2(L, M, S, lane, y, (u32)c8n & 255u);
+          if (c8n >= 256 || (c8n >= 16 && c8n < 32)) {
+            if (L.type == ZT_ICM || L.type == ZT_ISSE) *reinterpret_cast<uint4*>(L.ht + L.row_off) = L.row;
+          }
+          if (c8n >= 256) {
+            if (use_rcp) L.h = hcomp_recipes(R, lane, L.h, (u32)(c8n - 256), vm_c, hist, V.m, V.mmask, V.h, V.hmask);
+            else {
+              const int rc = vm2_run(V, (u32)(c8n - 256));
+              if (rc != ST_OK) { status = rc; break; }
+              L.h = V.h[(u32)lane & V.hmask];
+            }
+            M.hmap4 = 1; M.c8 = 1;
+            if (DEC) cbyte = c8n - 256;
+          }
+          else {
+            M.c8 = c8n;
+            if (c8n >= 16 && c8n < 32) M.hmap4 = (M.hmap4 & 0xf) << 5 | y << 4 | 1;
+            else M.hmap4 = (M.hmap4 & 0x1f0) | (((M.hmap4 & 0xf) * 2 + y) & 0xf);
+          }
+        }
+        if (DEC && status == ST_OK) {
+          if (C.out_pos < C.out_cap) { if (lane == 0) C.out[C.out_pos] = (u8)cbyte; }
+          else status = ST_FULL;
+          ++C.out_pos;
+        }
+      }
+      if (!DEC && status == ST_OK) {
+        enc_bit(C, lane, 1, 0);
+        if (C.status != ST_OK) status = C.status;
+      }
+      if (DEC && status == ST_OK && C.in_pos != C.in_end) status = ST_CORRUPT;
+      if (lane == 0) A.seg_out[B.seg_first + sg] = C.out_pos - out_start;
+    }
+    if (!DEC && status == ST_OK && C.status != ST_OK) status = C.status;
+    if (lane == 0) { A.status[blk] = status; A.out_len[blk] = C.out_pos; }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int zpq_code2_static_smem(void) { return S2_STATIC; }
+
+extern "C" cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int decode, int sm_count, int warps, int pw_bytes,
+                                        cudaStream_t st) {
+  if (nblk <= 0) return cudaSuccess;
+  const size_t smem = (size_t)S2_STATIC + (size_t)warps * pw_bytes;
+  static size_t attr_set = 0;
+  if (attr_set < smem) {
+    cudaError_t e = cudaFuncSetAttribute(zpq_code_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(zpq_code_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
+    if (e != cudaSuccess) return e;
+    attr_set = ZPQ_SMEM_MAX;
+  }
+  int ctas = (nblk + warps - 1) / warps;
+  if (ctas > sm_count) ctas = sm_count;            // persistent: one CTA per SM
+  if (decode) zpq_code_kernel2<true><<<ctas, warps * 32, smem, st>>>(*a, pw_bytes);
+  else zpq_code_kernel2<false><<<ctas, warps * 32, smem, st>>>(*a, pw_bytes);
+  return cudaGetLastError();
+}
