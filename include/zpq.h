@@ -104,7 +104,7 @@ int zpq_model_from_method(const char* method, const uint8_t* data, uint64_t n,
                           uint8_t* hdr, int cap, int* hlen);
 /* Diagnostics of the kernel plan for a header: info[0]=components, [1]=predict steps,
  * [2]=shared-memory bytes per block, [3]=1 if HCOMP runs as lane-parallel recipes
- * (0: bytecode interpreter), [4]=recipe rounds, [5]=ICM/ISSE tables left in HBM,
+ * (0: bytecode interpreter), [4]=recipe rounds, [5]=1 if the fast kernel takes this model,
  * [6]=generic-kernel steps, [7]=HCOMP bytes. */
 int zpq_model_describe(const uint8_t* hdr, int hlen, uint32_t info[8]);
 

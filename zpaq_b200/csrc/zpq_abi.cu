@@ -166,6 +166,10 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     }
     if (wave.empty()) { if (next < todo.size()) continue; break; }
     const int nb = (int)wave.size();
+    const bool allow_fast = ctx->kernel_version != 1;
+    std::stable_partition(wave.begin(), wave.end(), [&](int i) { return allow_fast && models[jobs[i].model].fast.ok != 0; });
+    int nfast = 0;
+    for (int i : wave) if (allow_fast && models[jobs[i].model].fast.ok != 0) ++nfast;
 
     std::vector<ZBlock> blocks(nb);
     std::vector<uint64_t> seg_len;
@@ -242,17 +246,27 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     CK(zpq_launch_init(&A, nb, st), "zpq_init_kernel launch");
     CK(cudaEventRecord(ev[2], st), "event");
     {
-      // v2 kernel: one CTA per SM; W warps share the 227 KB carve-out (static tables + W private regions)
-      uint32_t pw = 16;
-      for (int k = 0; k < nb; ++k) pw = std::max(pw, models[jobs[wave[k]].model].pw_bytes);
-      int warps = (int)std::min<uint64_t>(8, (ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem()) / pw);
-      if (ctx->kernel_version == 1 || warps < 1)
-        CK(zpq_launch_code(&A, nb, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
-      else
-        CK(zpq_launch_code2(&A, nb, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
+      // fast kernel for the models whose plan fits it (one CTA per SM, W warps sharing the 227 KB
+      // carve-out), generic kernel for the rest; the wave was ordered fast-first above
+      if (nfast > 0) {
+        uint32_t pw = 16;
+        for (int k = 0; k < nfast; ++k) pw = std::max(pw, models[jobs[wave[k]].model].fast.pw_bytes);
+        const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, (ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem()) / pw));
+        ZKernelArgs A1 = A;
+        A1.nblk = nfast;
+        CK(zpq_launch_code2(&A1, nfast, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
+        ++ctx->launches;
+      }
+      if (nb > nfast) {
+        ZKernelArgs A2 = A;
+        A2.blocks = A.blocks + nfast; A2.status = A.status + nfast; A2.out_len = A.out_len + nfast;
+        A2.counter = A.counter + 1; A2.nblk = nb - nfast;
+        CK(zpq_launch_code(&A2, nb - nfast, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
+        ++ctx->launches;
+      }
     }
     CK(cudaEventRecord(ev[3], st), "event");
-    ctx->launches += 2;
+    ++ctx->launches;   // init kernel
 
     std::vector<int32_t> status(nb);
     std::vector<uint64_t> out_len(nb), seg_out(nseg);
@@ -419,16 +433,13 @@ int zpq_model_bytes(const uint8_t* hdr, int hlen, uint64_t* bytes) {
 }
 
 // Diagnostics: info[0]=n, [1]=v2 steps, [2]=per-warp shared bytes, [3]=recipes ok, [4]=recipe rounds,
-// [5]=components whose ICM/ISSE table stays in HBM, [6]=v1 steps, [7]=HCOMP bytes
+// [5]=fast kernel usable, [6]=v1 steps, [7]=HCOMP bytes
 int zpq_model_describe(const uint8_t* hdr, int hlen, uint32_t info[8]) {
   ZModel* M = new ZModel(); std::vector<uint8_t> img; std::string e;
   const int rc = compile_model(hdr, hlen, M, &img, &e);
   if (rc == ZPQ_OK && info) {
-    info[0] = M->n; info[1] = M->nsteps2; info[2] = M->pw_bytes; info[3] = M->rcp.ok; info[4] = M->rcp.nrounds;
-    uint32_t spilled = 0;
-    for (uint32_t i = 0; i < M->n; ++i)
-      if ((M->comp[i].type == ZT_ICM || M->comp[i].type == ZT_ISSE) && M->smem_off[i] == 0xffffffffu) ++spilled;
-    info[5] = spilled; info[6] = M->nsteps; info[7] = M->prog_len;
+    info[0] = M->n; info[1] = M->fast.nsteps; info[2] = M->fast.pw_bytes; info[3] = M->rcp.ok; info[4] = M->rcp.nrounds;
+    info[5] = M->fast.ok; info[6] = M->nsteps; info[7] = M->prog_len;
   }
   delete M;
   return rc;

@@ -46,18 +46,29 @@ struct ZStep {
   uint32_t cm_off16;
 };
 
-// v2: one step = one uniform branch (16 bytes).
-struct alignas(16) ZStep2 {
-  uint8_t kind;     // ZK_*
-  uint8_t owner;    // lane that receives the result (all kinds but ZK_ISSE)
-  uint8_t j, k;     // input lanes: MIX2 j,k; SSE j; AVG j,k; MIX: j = first input, k = number of inputs
-  uint8_t rate;     // MIX learning rate
-  uint8_t q;        // MIX: slot in the per-lane weight registers (0xff: none, reload from memory)
-  uint8_t wt;       // AVG weight
-  uint8_t level;    // ZK_ISSE: lanes whose ZComp.step equals this value compute in this step
-  uint32_t cm_off16;// MIX weight table
-  uint32_t pad;
+// Fast-kernel plan: everything the per-bit loop needs sits in registers.
+// Step word: kind | owner<<3 | j<<8 | k<<13 | aux<<19 | q<<27
+//   ZK_ISSE : all ISSE lanes whose level equals (step index + 1) compute
+//   ZK_MIX  : owner, j = first input, k = number of inputs, aux = rate, q = weight-register slot
+//   ZK_MIX2 : owner, inputs j k        ZK_SSE : owner, input j, q = row-register slot
+//   ZK_AVG  : owner, inputs j k, aux = weight
+#define ZPQ_FAST_STEPS 16
+#define ZPQ_FAST_MIX 3
+#define ZPQ_FAST_SSE 2
+#define ZPQ_FAST_RCP 12
+#define ZSTEP_PACK(kind, owner, j, k, aux, q) \
+  ((uint32_t)(kind) | (uint32_t)(owner) << 3 | (uint32_t)(j) << 8 | (uint32_t)(k) << 13 | (uint32_t)(aux) << 19 | (uint32_t)(q) << 27)
+struct ZFast {
+  uint32_t ok;                        // 1: the model fits the fast kernel; 0: generic kernel only
+  uint32_t nsteps, nmix, nsse;
+  uint32_t sd[ZPQ_FAST_STEPS];
+  uint32_t mix_off16[ZPQ_FAST_MIX], mix_owner[ZPQ_FAST_MIX], mix_m[ZPQ_FAST_MIX], mix_j0[ZPQ_FAST_MIX], mix_rate[ZPQ_FAST_MIX];
+  uint32_t sse_off16[ZPQ_FAST_SSE], sse_owner[ZPQ_FAST_SSE], sse_mask[ZPQ_FAST_SSE];
+  uint32_t pw_bytes;                  // shared memory per block: all ICM (1 KB) and ISSE (2 KB) tables
+  uint32_t smem_off[ZPQ_MAX_LANES];   // byte offset of the lane's table inside the block's shared region
+  uint8_t level[ZPQ_MAX_LANES];       // ISSE lanes: dependency level (1 = fed by a phase-A component)
 };
+
 
 // Arena initialisation op (zpq_init_kernel).
 enum { ZF_ZERO = 0, ZF_CONST32, ZF_SSE, ZF_ICM, ZF_ISSE, ZF_BYTE1 };
@@ -101,12 +112,8 @@ struct ZModel {
   ZComp comp[ZPQ_MAX_LANES];
   ZStep steps[ZPQ_MAX_STEPS];
   ZFill fills[ZPQ_MAX_FILLS];
-  // ---- v2 kernel (zpq_kernels2.cu) ----
-  uint32_t pw_bytes;                    // per-warp shared memory this model wants
-  uint32_t smem_off[ZPQ_MAX_LANES];     // byte offset of the component's cm table in the warp's region, ~0u = stays in HBM
-  uint32_t nsteps2;
-  ZStep2 steps2[ZPQ_MAX_STEPS];         // kind-specialised step list (ZK_*)
-  uint8_t step2[ZPQ_MAX_LANES];          // ISSE lanes: level at which the lane computes
+  // ---- fast kernel plan (zpq_kernels2.cu) ----
+  ZFast fast;
   ZRecipes rcp;
 };
 

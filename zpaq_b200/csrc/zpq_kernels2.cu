@@ -6,13 +6,15 @@
 // dependent memory round trips, not by bandwidth.  So:
 //   * ICM / ISSE probability and weight tables (1-2 KB each) live in SHARED
 //     memory for the lifetime of the block; only hash rows, CM/SSE/MIX tables
-//     and the MATCH buffers stay in HBM.  One CTA per SM, W = 7 or 8 warps,
-//     the whole 227 KB carve-out used.
-//   * the dependent part of predict() is a list of kind-specialised steps
-//     (one uniform branch each): an ISSE level is 1 shuffle + 5 ALU ops.
-//   * MIX weight rows are fetched once per bit into registers (coalesced, lane
-//     l = weight l), reduced with redux.sync, and written back from the same
-//     registers in update().
+//     and the MATCH buffers stay in HBM.  One CTA per SM, W <= 8 warps, the
+//     whole 227 KB carve-out used (W = 7 for the 23-component level-5 model).
+//   * the dependent part of predict() is a fully unrolled list of at most 16
+//     steps whose descriptors sit in registers (no loads, one uniform branch
+//     per step): an ISSE level is 1 shuffle + 5 ALU ops.
+//   * MIX weight rows and SSE rows are fetched at the START of predict()
+//     (coalesced: lane l = element l) so their HBM/L2 latency overlaps the ISSE
+//     chain; MIX rows are reduced with redux.sync and written back from the
+//     same registers in update(); SSE picks its two buckets by shuffle.
 //   * HCOMP: programs of the makeConfig family are evaluated as per-lane
 //     recipes (zpq_hcomp.cpp), ~20 instructions per input byte per lane
 //     instead of ~9000 warp instructions of bytecode interpretation; any other
@@ -189,17 +191,17 @@ __device__ __noinline__ int vm2_run(Vm2& S, u32 input) {
 }
 
 // ---------------------------------------------------------------------------
-// Lane-parallel HCOMP: lane i folds its own op list into h (zpq_hcomp.cpp).
-// `hist` holds the last 8 input bytes (byte 0 = newest); older bytes come from
-// the M ring in HBM, which is still maintained exactly as the program's
-// prologue does (c-- *c=a ... *d=c).
+// Lane-parallel HCOMP: lane i folds its own op list (held in registers) into h
+// (zpq_hcomp.cpp).  `hist` holds the last 8 input bytes (byte 0 = newest);
+// older bytes come from the M ring in HBM, which is maintained exactly as the
+// program's prologue does (c-- *c=a ... *d=c).
 struct Rcp {
-  const u32* ops;      // [t][lane] in global memory (read-only, L1 resident)
+  u32 op[ZPQ_FAST_RCP];
   u32 start, base, round, len;
   u32 nrounds, needs_lastpos;
 };
 
-__device__ __forceinline__ u32 hcomp_recipes(const Rcp& R, int lane, u32 h, u32 byte, u32& c, u64& hist,
+__device__ __forceinline__ u32 hcomp_recipes(const Rcp& R, u32 h, u32 byte, u32& c, u64& hist,
                                              u8* m, u32 mmask, u32* H, u32 hmask) {
   // every lane issues the same stores (same address, same value: one transaction), so each
   // lane later reads its own writes and no intra-warp fence is needed
@@ -213,29 +215,34 @@ __device__ __forceinline__ u32 hcomp_recipes(const Rcp& R, int lane, u32 h, u32 
     const u32 hb = __shfl_sync(FULL, h, (int)R.base);
     if (R.round == r) {
       u32 acc = R.start == ZB_ZERO ? 0u : (R.start == ZB_OWN ? hold : hb);
-      for (u32 t = 0; t < R.len; ++t) {
-        const u32 w = __ldg(R.ops + t * 32 + lane);
-        const u32 op = w & 15u, src = (w >> 4) & 15u, arg = (w >> 8) & 255u, off = w >> 16;
-        u32 x = 0;
-        if (src == ZS_BYTE) {
-          if (off < 8) x = (u32)(hist >> (off * 8)) & arg;
-          else x = (u32)m[(c + off) & mmask] & arg;
+      bool skip = false;
+#pragma unroll
+      for (int t = 0; t < ZPQ_FAST_RCP; ++t) {
+        if (t < (int)R.len && !skip) {
+          const u32 w = R.op[t];
+          const u32 op = w & 15u, src = (w >> 4) & 15u, arg = (w >> 8) & 255u, off = w >> 16;
+          u32 x = 0;
+          if (src == ZS_BYTE) {
+            if (off < 8) x = (u32)(hist >> (off * 8)) & arg;
+            else x = (u32)m[(c + off) & mmask] & arg;
+          }
+          else if (src == ZS_POSAND) x = c & arg;
+          else if (src == ZS_POSMOD) x = arg ? c % arg : 0u;
+          else if (src == ZS_DIST) { x = H[(255u + arg) & hmask] - c; x = min(x, 255u); }
+          if (op == ZR_FOLD) acc = (acc + x + 512u) * 773u;
+          else if (op == ZR_SHL8ADD) acc = (acc << 8) + x;
+          else if (op == ZR_SHR) acc >>= arg;
+          else if (op == ZR_SHL) acc <<= arg;
+          else if (op == ZR_ROLL) acc = acc * off + byte + 1u;
+          else if (op == ZR_WORD) {
+            const u32 w2 = R.op[t + 1 < ZPQ_FAST_RCP ? t + 1 : t];
+            const u32 v2 = off & 255u, v3 = off >> 8, mult = w2 & 255u, first = (w2 >> 8) & 1u;
+            if ((((byte & arg) - v2) & 255u) < v3) acc = acc * mult + byte + 1u;
+            else acc = first ? 0u : hold_prev;
+            skip = true;
+          }
         }
-        else if (src == ZS_POSAND) x = c & arg;
-        else if (src == ZS_POSMOD) x = arg ? c % arg : 0u;
-        else if (src == ZS_DIST) { x = H[(255u + arg) & hmask] - c; x = min(x, 255u); }
-        if (op == ZR_FOLD) acc = (acc + x + 512u) * 773u;
-        else if (op == ZR_SHL8ADD) acc = (acc << 8) + x;
-        else if (op == ZR_SHR) acc >>= arg;
-        else if (op == ZR_SHL) acc <<= arg;
-        else if (op == ZR_ROLL) acc = acc * off + byte + 1u;
-        else if (op == ZR_WORD) {
-          const u32 w2 = __ldg(R.ops + (t + 1) * 32 + lane);
-          const u32 v2 = off & 255u, v3 = off >> 8, mult = w2 & 255u, first = (w2 >> 8) & 1u;
-          if ((((byte & arg) - v2) & 255u) < v3) acc = acc * mult + byte + 1u;
-          else acc = first ? 0u : hold_prev;
-          ++t;
-        }
+        else skip = false;
       }
       h = acc;
     }
@@ -245,8 +252,9 @@ __device__ __forceinline__ u32 hcomp_recipes(const Rcp& R, int lane, u32 h, u32 
 
 // ---------------------------------------------------------------------------
 struct Lane2 {
-  u32 type, a1, a2, a3, a4, a5, step;
-  u32* tab;        // cm table: generic pointer (shared memory copy, or HBM)
+  u32 type, a1, a2, a3, a4, a5, level;
+  u32 tabw;        // ICM/ISSE: word index of the cm table in shared memory
+  u32* gtab;       // CM / SSE / MIX2 / MATCH index: table in HBM
   u8* ht;
   u32 cm_mask, ht_mask, limit;
   u32 h;
@@ -291,44 +299,43 @@ __device__ __forceinline__ int dec_bit(Coder2& C, u32 p16) {
   return y;
 }
 
-#define ZPQ_MIXREG 3    // MIX components whose weight row is held in registers across predict/update
-
-struct Mod2 {
-  int n, nsteps;
-  const ZStep2* steps;     // global, read-only
-  u8* arena;
+// Register-resident plan of one block's model (uniform across the warp).
+struct Plan {
+  int n, nsteps, nmix, nsse;
+  u32 sd[ZPQ_FAST_STEPS];
+  int* mix_tab[ZPQ_FAST_MIX]; u32 mix_owner[ZPQ_FAST_MIX], mix_m[ZPQ_FAST_MIX], mix_j0[ZPQ_FAST_MIX], mix_rate[ZPQ_FAST_MIX];
+  const u32* sse_tab[ZPQ_FAST_SSE]; u32 sse_owner[ZPQ_FAST_SSE];
   int c8, hmap4;
-  int mixw[ZPQ_MIXREG], mixx[ZPQ_MIXREG];
-  u32 mixbase[ZPQ_MIXREG];
+  // per-bit values carried from predict to update
+  // (scalars, not arrays: they are selected by a run-time slot number and must stay in registers)
+  int mixw0, mixw1, mixw2, mixx0, mixx1, mixx2;
+  u32 mixbase[ZPQ_FAST_MIX];
+  u32 sserow0, sserow1;
 };
-
-__device__ __forceinline__ ZStep2 ld_step(const ZStep2* p) {
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-  ZStep2 s;
-  s.kind = v.x & 255; s.owner = (v.x >> 8) & 255; s.j = (v.x >> 16) & 255; s.k = v.x >> 24;
-  s.rate = v.y & 255; s.q = (v.y >> 8) & 255; s.wt = (v.y >> 16) & 255; s.level = v.y >> 24;
-  s.cm_off16 = v.z; s.pad = v.w;
-  return s;
-}
+#define MIXW_GET(M, q) ((q) == 0 ? (M).mixw0 : ((q) == 1 ? (M).mixw1 : (M).mixw2))
+#define MIXX_GET(M, q) ((q) == 0 ? (M).mixx0 : ((q) == 1 ? (M).mixx1 : (M).mixx2))
+#define MIXW_SET(M, q, v) do { if ((q) == 0) (M).mixw0 = (v); else if ((q) == 1) (M).mixw1 = (v); else (M).mixw2 = (v); } while (0)
+#define MIXX_SET(M, q, v) do { if ((q) == 0) (M).mixx0 = (v); else if ((q) == 1) (M).mixx1 = (v); else (M).mixx2 = (v); } while (0)
 
 // Predictor::predict0 (libzpaq.cpp:1854-1951)
-__device__ __forceinline__ int predict2(Lane2& L, Mod2& M, const Tabs& S, int lane) {
+__device__ __forceinline__ int predict2(Lane2& L, Plan& M, const Tabs& S, const u32* sm32, int lane) {
   const int c8 = M.c8, hmap4 = M.hmap4;
   const bool nib = (c8 == 1) || ((c8 & 0xf0) == 16);
+  // ---- phase A: per-lane table lookups ----
   if (L.type == ZT_ICM || L.type == ZT_ISSE) {
     if (nib) d_find(L.ht, L.ht_mask, (int)L.a1 + 2, L.h + 16u * (u32)c8, L.row, L.row_off);
     L.bh = row_get(L.row, hmap4 & 15);
     if (L.type == ZT_ISSE) {
-      const uint2 w = *reinterpret_cast<const uint2*>(L.tab + L.bh * 2);
+      const uint2 w = *reinterpret_cast<const uint2*>(sm32 + L.tabw + L.bh * 2);
       L.v0 = w.x; L.v1 = w.y;
     } else {
-      L.v0 = L.tab[L.bh];
+      L.v0 = sm32[L.tabw + L.bh];
       L.p = t_stretch(S, L.v0 >> 8);
     }
   }
   else if (L.type == ZT_CM) {
     L.cxt = (L.h ^ (u32)hmap4) & L.cm_mask;
-    L.v0 = L.tab[L.cxt];
+    L.v0 = L.gtab[L.cxt];
     L.p = t_stretch(S, L.v0 >> 17);
   }
   else if (L.type == ZT_MATCH) {
@@ -340,55 +347,75 @@ __device__ __forceinline__ int predict2(Lane2& L, Mod2& M, const Tabs& S, int la
   }
   else if (L.type == ZT_MIX2) {
     L.cxt = (L.h + (u32)(c8 & (int)L.a5)) & L.cm_mask;
-    L.v0 = reinterpret_cast<const u16*>(L.tab)[L.cxt];
+    L.v0 = reinterpret_cast<const u16*>(L.gtab)[L.cxt];
   }
   else if (L.type == ZT_MIX) L.cxt = ((L.h + (u32)(c8 & (int)L.a5)) & L.cm_mask) * L.a3;
-  else if (L.type == ZT_SSE) L.cxt = (L.h + (u32)c8) * 32u;
-
-  for (int s = 0; s < M.nsteps; ++s) {
-    const ZStep2 st = ld_step(M.steps + s);
-    if (st.kind == ZK_ISSE) {
-      const int pj = __shfl_sync(FULL, L.p, (int)L.a2 & 31);
-      if (L.type == ZT_ISSE && L.step == st.level) {
-        L.xj = pj;
-        L.p = clamp2k(((int)L.v0 * pj + (int)L.v1 * 64) >> 16);
-      }
-    }
-    else if (st.kind == ZK_MIX) {
-      const u32 base = __shfl_sync(FULL, L.cxt, (int)st.owner);
-      const int x = __shfl_sync(FULL, L.p, ((int)st.j + lane) & 31);
-      int w = 0;
-      if (lane < (int)st.k) w = (reinterpret_cast<const int*>(M.arena + (u64)st.cm_off16 * 16))[base + lane];
-      const int sum = __reduce_add_sync(FULL, (w >> 8) * x);
-      if (lane == (int)st.owner) L.p = clamp2k(sum >> 8);
+  else if (L.type == ZT_SSE) L.cxt = ((L.h + (u32)c8) * 32u) & L.cm_mask;
+  // ---- early coalesced row fetches (latency overlaps the ISSE chain) ----
 #pragma unroll
-      for (int q = 0; q < ZPQ_MIXREG; ++q) if (st.q == q) { M.mixw[q] = w; M.mixx[q] = x; M.mixbase[q] = base; }
+  for (int q = 0; q < ZPQ_FAST_MIX; ++q)
+    if (q < M.nmix) {
+      const u32 base = __shfl_sync(FULL, L.cxt, (int)M.mix_owner[q]);
+      M.mixbase[q] = base;
+      const int wq = lane < (int)M.mix_m[q] ? M.mix_tab[q][base + lane] : 0;
+      MIXW_SET(M, q, wq);
     }
-    else if (st.kind == ZK_MIX2) {
-      const int pj = __shfl_sync(FULL, L.p, (int)st.j);
-      const int pk = __shfl_sync(FULL, L.p, (int)st.k);
-      if (lane == (int)st.owner) {
-        L.xj = pj; L.xk = pk;
-        const int w = (int)L.v0;
-        L.p = (w * pj + (65536 - w) * pk) >> 16;
+#pragma unroll
+  for (int r = 0; r < ZPQ_FAST_SSE; ++r)
+    if (r < M.nsse) {
+      const u32 rb = __shfl_sync(FULL, L.cxt, (int)M.sse_owner[r]);
+      const u32 rowv = M.sse_tab[r][rb + lane];
+      if (r == 0) M.sserow0 = rowv; else M.sserow1 = rowv;
+    }
+  // ---- dependent components ----
+#pragma unroll
+  for (int s = 0; s < ZPQ_FAST_STEPS; ++s) {
+    if (s < M.nsteps) {
+      const u32 d = M.sd[s];
+      const u32 kind = d & 7u;
+      const int owner = (int)((d >> 3) & 31u), sj = (int)((d >> 8) & 31u), sk = (int)((d >> 13) & 63u);
+      if (kind == ZK_ISSE) {
+        const int pj = __shfl_sync(FULL, L.p, (int)L.a2 & 31);
+        if (L.level == (u32)(s + 1)) {
+          L.xj = pj;
+          L.p = clamp2k(((int)L.v0 * pj + (int)L.v1 * 64) >> 16);
+        }
       }
-    }
-    else if (st.kind == ZK_SSE) {
-      const int pj = __shfl_sync(FULL, L.p, (int)st.j);
-      if (lane == (int)st.owner) {
+      else if (kind == ZK_MIX) {
+        const int x = __shfl_sync(FULL, L.p, (sj + lane) & 31);
+        const u32 q = d >> 27;
+        const int w = MIXW_GET(M, q);
+        MIXX_SET(M, q, x);
+        const int sum = __reduce_add_sync(FULL, (w >> 8) * x);
+        if (lane == owner) L.p = clamp2k(sum >> 8);
+      }
+      else if (kind == ZK_MIX2) {
+        const int pj = __shfl_sync(FULL, L.p, sj);
+        const int pk = __shfl_sync(FULL, L.p, sk & 31);
+        if (lane == owner) {
+          L.xj = pj; L.xk = pk;
+          const int w = (int)L.v0;
+          L.p = (w * pj + (65536 - w) * pk) >> 16;
+        }
+      }
+      else if (kind == ZK_SSE) {
+        const int pj = __shfl_sync(FULL, L.p, sj);
         int pq = min(max(pj + 992, 0), 1983);
         const int wt = pq & 63;
         pq >>= 6;
-        const u32 c0 = (L.cxt + (u32)pq) & L.cm_mask, c1 = (L.cxt + (u32)pq + 1u) & L.cm_mask;
-        const u32 q0 = L.tab[c0], q1 = L.tab[c1];
-        L.p = t_stretch(S, (u32)(((int)(q0 >> 10) * (64 - wt) + (int)(q1 >> 10) * wt) >> 13));
-        if (wt >> 5) { L.cxt = c1; L.v0 = q1; } else { L.cxt = c0; L.v0 = q0; }
+        const u32 row = (d >> 27) == 0 ? M.sserow0 : M.sserow1;
+        const u32 q0 = __shfl_sync(FULL, row, pq), q1 = __shfl_sync(FULL, row, pq + 1);
+        if (lane == owner) {
+          L.p = t_stretch(S, (u32)(((int)(q0 >> 10) * (64 - wt) + (int)(q1 >> 10) * wt) >> 13));
+          if (wt >> 5) { L.cxt += (u32)pq + 1u; L.v0 = q1; } else { L.cxt += (u32)pq; L.v0 = q0; }
+        }
       }
-    }
-    else {   // ZK_AVG
-      const int pj = __shfl_sync(FULL, L.p, (int)st.j);
-      const int pk = __shfl_sync(FULL, L.p, (int)st.k);
-      if (lane == (int)st.owner) L.p = (pj * (int)st.wt + pk * (256 - (int)st.wt)) >> 8;
+      else {   // ZK_AVG
+        const int pj = __shfl_sync(FULL, L.p, sj);
+        const int pk = __shfl_sync(FULL, L.p, sk & 31);
+        const int wt = (int)((d >> 19) & 255u);
+        if (lane == owner) L.p = (pj * wt + pk * (256 - wt)) >> 8;
+      }
     }
   }
   const int pfinal = __shfl_sync(FULL, L.p, M.n - 1);
@@ -396,7 +423,7 @@ __device__ __forceinline__ int predict2(Lane2& L, Mod2& M, const Tabs& S, int la
 }
 
 // Predictor::update0 component part (libzpaq.cpp:1954-2052)
-__device__ __forceinline__ void update2(Lane2& L, Mod2& M, const Tabs& S, int lane, int y, u32 byte_done) {
+__device__ __forceinline__ void update2(Lane2& L, Plan& M, const Tabs& S, u32* sm32, int lane, int y, u32 byte_done) {
   const int hmap4 = M.hmap4;
   if (L.type == ZT_ICM || L.type == ZT_ISSE) {
     const u32 nx = ((u32)S.ns[L.bh] >> (8 * y)) & 255u;
@@ -405,25 +432,25 @@ __device__ __forceinline__ void update2(Lane2& L, Mod2& M, const Tabs& S, int la
       const int err = y * 32767 - t_squash(S, L.p);
       const int w0 = clamp512k((int)L.v0 + ((err * L.xj + (1 << 12)) >> 13));
       const int w1 = clamp512k((int)L.v1 + ((err + 16) >> 5));
-      *reinterpret_cast<uint2*>(L.tab + L.bh * 2) = make_uint2((u32)w0, (u32)w1);
+      *reinterpret_cast<uint2*>(sm32 + L.tabw + L.bh * 2) = make_uint2((u32)w0, (u32)w1);
     } else {
       const u32 pn = L.v0;
-      L.tab[L.bh] = pn + (u32)(((int)(y * 32767 - (int)(pn >> 8))) >> 2);
+      sm32[L.tabw + L.bh] = pn + (u32)(((int)(y * 32767 - (int)(pn >> 8))) >> 2);
     }
   }
-  else if (L.type == ZT_CM || L.type == ZT_SSE) {
+  else if (L.type == ZT_CM || L.type == ZT_SSE) {   // train(), libzpaq.h:1151-1157
     const u32 pn = L.v0;
     const u32 count = pn & 0x3ffu;
     const int err = y * 32767 - (int)(pn >> 17);
     const u32 prod = (u32)err * ((u32)S.dt[count] * 2u);
-    L.tab[L.cxt] = pn + (prod & 0xfffffc00u) + (count < L.limit ? 1u : 0u);
+    L.gtab[L.cxt] = pn + (prod & 0xfffffc00u) + (count < L.limit ? 1u : 0u);
   }
   else if (L.type == ZT_MIX2) {
     const int err = ((y * 32767 - t_squash(S, L.p)) * (int)L.a4) >> 5;
     int w = (int)L.v0;
     w += (err * (L.xj - L.xk) + (1 << 12)) >> 13;
     w = min(max(w, 0), 65535);
-    reinterpret_cast<u16*>(L.tab)[L.cxt] = (u16)w;
+    reinterpret_cast<u16*>(L.gtab)[L.cxt] = (u16)w;
   }
   else if (L.type == ZT_MATCH) {
     if ((int)L.mc != y) L.ma = 0;
@@ -431,7 +458,7 @@ __device__ __forceinline__ void update2(Lane2& L, Mod2& M, const Tabs& S, int la
       L.mbit = 0;
       L.ht[L.mpos] = (u8)byte_done;
       L.mpos = (L.mpos + 1) & L.ht_mask;
-      u32* idx = L.tab + (L.h & L.cm_mask);
+      u32* idx = L.gtab + (L.h & L.cm_mask);
       if (L.ma == 0) {
         L.mb = L.mpos - *idx;
         if (L.mb & L.ht_mask)
@@ -443,24 +470,15 @@ __device__ __forceinline__ void update2(Lane2& L, Mod2& M, const Tabs& S, int la
       L.mpred = L.ht[(L.mpos - L.mb) & L.ht_mask];
     }
   }
-  // MIX rows
-  for (int s = 0; s < M.nsteps; ++s) {
-    const ZStep2 st = ld_step(M.steps + s);
-    if (st.kind != ZK_MIX) continue;
-    const int e0 = ((y * 32767 - t_squash(S, L.p)) * (int)st.rate) >> 4;
-    const int err = __shfl_sync(FULL, e0, (int)st.owner);
-    int w = 0, x = 0; u32 base = 0;
-    bool have = false;
+  // MIX rows: lane l trains weight l from the registers loaded in predict
 #pragma unroll
-    for (int q = 0; q < ZPQ_MIXREG; ++q) if (st.q == q) { w = M.mixw[q]; x = M.mixx[q]; base = M.mixbase[q]; have = true; }
-    int* wt = reinterpret_cast<int*>(M.arena + (u64)st.cm_off16 * 16);
-    if (!have) {
-      base = __shfl_sync(FULL, L.cxt, (int)st.owner);
-      x = __shfl_sync(FULL, L.p, ((int)st.j + lane) & 31);
-      if (lane < (int)st.k) w = wt[base + lane];
+  for (int q = 0; q < ZPQ_FAST_MIX; ++q)
+    if (q < M.nmix) {
+      const int e0 = ((y * 32767 - t_squash(S, L.p)) * (int)M.mix_rate[q]) >> 4;
+      const int err = __shfl_sync(FULL, e0, (int)M.mix_owner[q]);
+      if (lane < (int)M.mix_m[q])
+        M.mix_tab[q][M.mixbase[q] + lane] = clamp512k(MIXW_GET(M, q) + ((err * MIXX_GET(M, q) + (1 << 12)) >> 13));
     }
-    if (lane < (int)st.k) wt[base + lane] = clamp512k(w + ((err * x + (1 << 12)) >> 13));
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -487,9 +505,10 @@ __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, 
   S.dt = reinterpret_cast<const u16*>(smem + S2_DT);
   S.ns = reinterpret_cast<const u16*>(smem + S2_NS);
   S.dt2k = reinterpret_cast<const u16*>(smem + S2_DT2K);
+  u32* sm32 = reinterpret_cast<u32*>(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* wsm = smem + S2_STATIC + (size_t)warp * pw_bytes;   // this warp's private region
+  const u32 wbase = (u32)(S2_STATIC + warp * pw_bytes) / 4u;      // this warp's private region (word index)
 
   for (;;) {
     int blk = 0;
@@ -499,12 +518,26 @@ __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, 
 
     const ZBlock B = A.blocks[blk];
     const ZModel* __restrict__ ZM = A.models + B.model;
-    Mod2 M;
-    M.n = (int)ZM->n; M.nsteps = (int)ZM->nsteps2; M.steps = ZM->steps2;
-    M.arena = A.arena + B.arena_off;
-    M.c8 = 1; M.hmap4 = 1;
+    u8* const arena = A.arena + B.arena_off;
+    Plan M;
+    M.n = (int)ZM->n; M.nsteps = (int)ZM->fast.nsteps; M.nmix = (int)ZM->fast.nmix; M.nsse = (int)ZM->fast.nsse;
 #pragma unroll
-    for (int q = 0; q < ZPQ_MIXREG; ++q) { M.mixw[q] = 0; M.mixx[q] = 0; M.mixbase[q] = 0; }
+    for (int s = 0; s < ZPQ_FAST_STEPS; ++s) M.sd[s] = ZM->fast.sd[s];
+#pragma unroll
+    for (int q = 0; q < ZPQ_FAST_MIX; ++q) {
+      M.mix_tab[q] = reinterpret_cast<int*>(arena + (u64)ZM->fast.mix_off16[q] * 16);
+      M.mix_owner[q] = ZM->fast.mix_owner[q]; M.mix_m[q] = ZM->fast.mix_m[q];
+      M.mix_j0[q] = ZM->fast.mix_j0[q]; M.mix_rate[q] = ZM->fast.mix_rate[q];
+      M.mixbase[q] = 0;
+    }
+    M.mixw0 = M.mixw1 = M.mixw2 = M.mixx0 = M.mixx1 = M.mixx2 = 0;
+    M.sserow0 = M.sserow1 = 0;
+#pragma unroll
+    for (int r = 0; r < ZPQ_FAST_SSE; ++r) {
+      M.sse_tab[r] = reinterpret_cast<const u32*>(arena + (u64)ZM->fast.sse_off16[r] * 16);
+      M.sse_owner[r] = ZM->fast.sse_owner[r];
+    }
+    M.c8 = 1; M.hmap4 = 1;
 
     // ---- lane <-> component ----
     Lane2 L;
@@ -514,45 +547,42 @@ __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, 
       else { cd.type = ZT_NONE; cd.a1 = cd.a2 = cd.a3 = cd.a4 = cd.a5 = 0; cd.step = 0; cd.cm_off16 = cd.ht_off16 = 0;
              cd.cm_mask = cd.ht_mask = cd.limit = 0; }
       L.type = cd.type; L.a1 = cd.a1; L.a2 = cd.a2; L.a3 = cd.a3; L.a4 = cd.a4; L.a5 = cd.a5;
-      L.step = (lane < M.n) ? ZM->step2[lane] : 0;
-      L.tab = reinterpret_cast<u32*>(M.arena + (u64)cd.cm_off16 * 16);
-      L.ht = M.arena + (u64)cd.ht_off16 * 16;
+      L.level = (lane < M.n) ? ZM->fast.level[lane] : 0;
+      L.gtab = reinterpret_cast<u32*>(arena + (u64)cd.cm_off16 * 16);
+      L.ht = arena + (u64)cd.ht_off16 * 16;
       L.cm_mask = cd.cm_mask; L.ht_mask = cd.ht_mask; L.limit = cd.limit;
       L.h = 0;
       L.p = (cd.type == ZT_CONS) ? ((int)cd.a1 - 128) * 4 : 0;
       L.xj = L.xk = 0; L.cxt = 0; L.v0 = L.v1 = 0; L.bh = 0;
       L.row = make_uint4(0, 0, 0, 0); L.row_off = 0;
       L.ma = L.mb = L.mpos = L.mbit = L.mc = 0; L.mpred = 0;
-      // ICM / ISSE tables that got a shared-memory slot: initialise it here
-      // (Predictor::init values, libzpaq.cpp:1786-1789, 1829-1833) and use it.
-      const u32 so = (lane < M.n) ? ZM->smem_off[lane] : 0xffffffffu;
+      L.tabw = wbase + ((lane < M.n) ? ZM->fast.smem_off[lane] : 0u) / 4u;
+      // ICM / ISSE tables live in shared memory: Predictor::init values (libzpaq.cpp:1786-1789, 1829-1833)
       __syncwarp();
       for (int src = 0; src < M.n; ++src) {
-        const u32 o = __shfl_sync(FULL, so, src);
         const u32 ty = __shfl_sync(FULL, L.type, src);
-        if (o == 0xffffffffu) continue;
-        u32* dst = reinterpret_cast<u32*>(wsm + o);
-        if (ty == ZT_ICM) for (int i = lane; i < 256; i += 32) dst[i] = A.tables->icm_init[i];
-        else for (int i = lane; i < 512; i += 32) dst[i] = A.tables->isse_init[i];
+        const u32 tw = __shfl_sync(FULL, L.tabw, src);
+        if (ty == ZT_ICM) for (int i = lane; i < 256; i += 32) sm32[tw + i] = A.tables->icm_init[i];
+        else if (ty == ZT_ISSE) for (int i = lane; i < 512; i += 32) sm32[tw + i] = A.tables->isse_init[i];
       }
-      if (so != 0xffffffffu) L.tab = reinterpret_cast<u32*>(wsm + so);
       __syncwarp();
     }
 
     // ---- HCOMP ----
     const bool use_rcp = ZM->rcp.ok != 0;
     Rcp R;
-    R.ops = &ZM->rcp.ops[0][0];
     R.start = R.base = R.round = R.len = 0;
     R.nrounds = ZM->rcp.nrounds; R.needs_lastpos = ZM->rcp.needs_lastpos;
+#pragma unroll
+    for (int t = 0; t < ZPQ_FAST_RCP; ++t) R.op[t] = (use_rcp && lane < M.n) ? ZM->rcp.ops[t][lane] : 0u;
     if (use_rcp && lane < M.n) { R.start = ZM->rcp.start[lane]; R.base = ZM->rcp.base[lane]; R.round = ZM->rcp.round[lane]; R.len = ZM->rcp.len[lane]; }
     if (lane >= M.n) R.round = 0xffu;
     u32 vm_c = 0; u64 hist = 0;
     Vm2 V;
     V.a = V.b = V.c = V.d = V.f = 0;
-    V.m = M.arena + (u64)ZM->m_off16 * 16;
-    V.h = reinterpret_cast<u32*>(M.arena + (u64)ZM->h_off16 * 16);
-    V.r = reinterpret_cast<u32*>(M.arena + (u64)ZM->r_off16 * 16);
+    V.m = arena + (u64)ZM->m_off16 * 16;
+    V.h = reinterpret_cast<u32*>(arena + (u64)ZM->h_off16 * 16);
+    V.r = reinterpret_cast<u32*>(arena + (u64)ZM->r_off16 * 16);
     V.mmask = ZM->m_mask; V.hmask = ZM->h_mask;
     V.len = (int)ZM->prog_len;
     V.code = A.progs + ZM->prog_off + ZPQ_GUARD_LO;
@@ -587,7 +617,7 @@ __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, 
           if (eos) { if (C.curr != 0) status = ST_EOS; break; }
         }
         for (int bit = 7; bit >= 0; --bit) {
-          const u32 p16 = (u32)predict2(L, M, S, lane) * 2u + 1u;
+          const u32 p16 = (u32)predict2(L, M, S, sm32, lane) * 2u + 1u;
           int y;
           if constexpr (!DEC) { y = (cbyte >> bit) & 1; enc_bit(C, lane, y, p16); }
           else {
@@ -595,12 +625,12 @@ __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, 
             if (C.status != ST_OK) { status = C.status; break; }
           }
           const int c8n = M.c8 * 2 + y;
-          update2(L, M, S, lane, y, (u32)c8n & 255u);
+          update2(L, M, S, sm32, lane, y, (u32)c8n & 255u);
           if (c8n >= 256 || (c8n >= 16 && c8n < 32)) {
             if (L.type == ZT_ICM || L.type == ZT_ISSE) *reinterpret_cast<uint4*>(L.ht + L.row_off) = L.row;
           }
           if (c8n >= 256) {
-            if (use_rcp) L.h = hcomp_recipes(R, lane, L.h, (u32)(c8n - 256), vm_c, hist, V.m, V.mmask, V.h, V.hmask);
+            if (use_rcp) L.h = hcomp_recipes(R, L.h, (u32)(c8n - 256), vm_c, hist, V.m, V.mmask, V.h, V.hmask);
             else {
               const int rc = vm2_run(V, (u32)(c8n - 256));
               if (rc != ST_OK) { status = rc; break; }
@@ -641,13 +671,13 @@ extern "C" cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int deco
                                         cudaStream_t st) {
   if (nblk <= 0) return cudaSuccess;
   const size_t smem = (size_t)S2_STATIC + (size_t)warps * pw_bytes;
-  static size_t attr_set = 0;
-  if (attr_set < smem) {
+  static bool attr_set = false;
+  if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(zpq_code_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(zpq_code_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
     if (e != cudaSuccess) return e;
-    attr_set = ZPQ_SMEM_MAX;
+    attr_set = true;
   }
   int ctas = (nblk + warps - 1) / warps;
   if (ctas > sm_count) ctas = sm_count;            // persistent: one CTA per SM

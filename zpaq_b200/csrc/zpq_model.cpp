@@ -300,73 +300,68 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
   if (lay.pos16 >= ((uint64_t)1 << 32)) return fail(err, ZPQ_E_NOMEM, "Out of memory");
   M->arena_bytes = ((lay.pos16 * 16) + 255) & ~(uint64_t)255;
 
-  // ================= v2 kernel plan =================
-  // (1) kind-specialised step list: ISSE components are grouped by dependency
-  //     level, every other dependent component gets a step of its own.
+  // ================= fast kernel plan =================
+  // ISSE components are grouped by dependency level (one step per level); every other
+  // dependent component gets a step of its own.  The plan is only valid (fast.ok) when it
+  // fits the register budgets of zpq_kernels2.cu; otherwise the generic kernel codes the block.
   {
+    ZFast& F = M->fast;
+    memset(&F, 0, sizeof(F));
+    bool ok = true;
     int rdy[ZPQ_MAX_LANES];
-    int ns2 = 0, nmixreg = 0;
+    int ns = 0;
     const uint8_t* q = hdr + 7;
-    for (int i = 0; i < n; ++i) {
-      rdy[i] = 0; M->step2[i] = 0;
-      auto add = [&](uint8_t kind) -> ZStep2* {
-        if (ns2 >= ZPQ_MAX_STEPS) return nullptr;
-        ZStep2* s = &M->steps2[ns2++];
-        memset(s, 0, sizeof(*s));
-        s->kind = kind; s->owner = (uint8_t)i; s->q = 0xff; s->level = (uint8_t)ns2;
-        return s;
-      };
-      ZStep2* s = nullptr;
+    for (int i = 0; i < n && ok; ++i) {
+      rdy[i] = 0; F.level[i] = 0;
       switch (q[0]) {
         case ZT_ISSE: {
           const int need = rdy[q[2]];
           int at = -1;
-          for (int k = need; k < ns2; ++k) if (M->steps2[k].kind == ZK_ISSE) { at = k; break; }
-          if (at < 0) { s = add(ZK_ISSE); if (!s) return fail(err, ZPQ_E_UNSUPPORTED, "too many predict steps"); at = ns2 - 1; }
-          rdy[i] = at + 1; M->step2[i] = (uint8_t)(at + 1);
+          for (int k = need; k < ns; ++k) if ((F.sd[k] & 7) == ZK_ISSE) { at = k; break; }
+          if (at < 0) { if (ns >= ZPQ_FAST_STEPS) { ok = false; break; } F.sd[ns] = ZSTEP_PACK(ZK_ISSE, 0, 0, 0, 0, 0); at = ns++; }
+          rdy[i] = at + 1; F.level[i] = (uint8_t)(at + 1);
           break;
         }
         case ZT_MIX:
-          s = add(ZK_MIX); if (!s) return fail(err, ZPQ_E_UNSUPPORTED, "too many predict steps");
-          s->j = q[2]; s->k = q[3]; s->rate = q[4]; s->cm_off16 = M->comp[i].cm_off16;
-          if (nmixreg < ZPQ_MIXREG_HOST) s->q = (uint8_t)nmixreg++;
-          rdy[i] = ns2;
+          if (ns >= ZPQ_FAST_STEPS || F.nmix >= ZPQ_FAST_MIX) { ok = false; break; }
+          F.mix_off16[F.nmix] = M->comp[i].cm_off16; F.mix_owner[F.nmix] = i; F.mix_m[F.nmix] = q[3];
+          F.mix_j0[F.nmix] = q[2]; F.mix_rate[F.nmix] = q[4];
+          F.sd[ns++] = ZSTEP_PACK(ZK_MIX, i, q[2], q[3], q[4], F.nmix);
+          ++F.nmix; rdy[i] = ns;
           break;
         case ZT_MIX2:
-          s = add(ZK_MIX2); if (!s) return fail(err, ZPQ_E_UNSUPPORTED, "too many predict steps");
-          s->j = q[2]; s->k = q[3]; rdy[i] = ns2;
+          if (ns >= ZPQ_FAST_STEPS) { ok = false; break; }
+          F.sd[ns++] = ZSTEP_PACK(ZK_MIX2, i, q[2], q[3], 0, 0); rdy[i] = ns;
           break;
         case ZT_SSE:
-          s = add(ZK_SSE); if (!s) return fail(err, ZPQ_E_UNSUPPORTED, "too many predict steps");
-          s->j = q[2]; rdy[i] = ns2;
+          if (ns >= ZPQ_FAST_STEPS || F.nsse >= ZPQ_FAST_SSE) { ok = false; break; }
+          F.sse_off16[F.nsse] = M->comp[i].cm_off16; F.sse_owner[F.nsse] = i; F.sse_mask[F.nsse] = M->comp[i].cm_mask;
+          F.sd[ns++] = ZSTEP_PACK(ZK_SSE, i, q[2], 0, 0, F.nsse);
+          ++F.nsse; rdy[i] = ns;
           break;
         case ZT_AVG:
-          s = add(ZK_AVG); if (!s) return fail(err, ZPQ_E_UNSUPPORTED, "too many predict steps");
-          s->j = q[1]; s->k = q[2]; s->wt = q[3]; rdy[i] = ns2;
+          if (ns >= ZPQ_FAST_STEPS) { ok = false; break; }
+          F.sd[ns++] = ZSTEP_PACK(ZK_AVG, i, q[1], q[2], q[3], 0); rdy[i] = ns;
           break;
         default: break;
       }
       q += kCompLen[q[0]];
     }
-    M->nsteps2 = ns2;
-    // (2) shared-memory slots for ICM (1 KB) and ISSE (2 KB) tables, shallowest first; what
-    //     does not fit the per-warp budget of a 7-warp CTA stays in HBM (deep ISSEs have slack).
-    const uint32_t budget = ((ZPQ_SMEM_MAX - 38528) / 7) & ~15u;
+    F.nsteps = ns;
     uint32_t used = 0;
-    for (int i = 0; i < n; ++i) M->smem_off[i] = 0xffffffffu;
-    for (int level = 0; level <= ns2; ++level)
-      for (int i = 0; i < n; ++i) {
-        const int t = M->comp[i].type;
-        if (t != ZT_ICM && t != ZT_ISSE) continue;
-        if ((int)M->step2[i] != level) continue;
-        const uint32_t sz = t == ZT_ICM ? 1024 : 2048;
-        if (used + sz > budget) continue;
-        M->smem_off[i] = used; used += sz;
-      }
-    M->pw_bytes = (used + 15) & ~15u;
+    for (int i = 0; i < n; ++i) {
+      const int t = M->comp[i].type;
+      F.smem_off[i] = 0;
+      if (t == ZT_ICM) { F.smem_off[i] = used; used += 1024; }
+      else if (t == ZT_ISSE) { F.smem_off[i] = used; used += 2048; }
+    }
+    F.pw_bytes = std::max<uint32_t>(16, used);
+    if (F.pw_bytes > ZPQ_SMEM_MAX - 38528) ok = false;
+    F.ok = ok ? 1 : 0;
   }
   // (3) lane-parallel HCOMP recipes (zpq_hcomp.cpp)
   build_recipes(M, hdr + pos, prog_len);
+  if (M->rcp.ok) for (uint32_t l = 0; l < M->n; ++l) if (M->rcp.len[l] > ZPQ_FAST_RCP) M->fast.ok = 0;
   return ZPQ_OK;
 }
 
