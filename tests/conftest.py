@@ -12,9 +12,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _make_ctx(kernel):
+    import zpaq_b200 as Z
+    old = os.environ.get("ZPQ_KERNEL")
+    os.environ["ZPQ_KERNEL"] = kernel
+    try:
+        return Z.Context(0)   # raises if there is no GPU: GPU tests must not silently pass
+    finally:
+        if old is None:
+            del os.environ["ZPQ_KERNEL"]
+        else:
+            os.environ["ZPQ_KERNEL"] = old
+
+
 @pytest.fixture(scope="session")
 def ctx():
-    import zpaq_b200 as Z
-    c = Z.Context(0)   # raises if there is no GPU: GPU tests must not silently pass
+    """Production configuration: skewed-pipeline encoder + fast sequential decoder."""
+    c = _make_ctx("3")
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="session", params=["3", "2", "1"], ids=["pipeline", "fast", "generic"])
+def kctx(request):
+    """Every kernel tier: 3 = production, 2 = fast sequential kernel for both directions, 1 = generic kernel."""
+    c = _make_ctx(request.param)
     yield c
     c.close()

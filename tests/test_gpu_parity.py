@@ -24,7 +24,8 @@ def _roundtrip(ctx, hdr, payloads):
 
 @pytest.mark.parametrize("method", ["4", "5", CFG_ALL_METHOD])
 @pytest.mark.parametrize("kind", [0, 1, 2, 3])
-def test_method_parity(ctx, method, kind):
+def test_method_parity(kctx, method, kind):
+    ctx = kctx
     payloads = [O.gen_block(kind, 100 + i, n) for i, n in enumerate((0, 1, 7, 300, 5000, 40000))]
     hdrs = {}
     for p in payloads:

@@ -64,7 +64,7 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   uint64_t launches = 0;
-  int kernel_version = 2;      // ZPQ_KERNEL=1 selects the generic v1 kernel (A/B testing)
+  int kernel_version = 3;      // ZPQ_KERNEL=1: generic kernel only; 2: no skewed-pipeline encoder (A/B testing)
 };
 
 namespace {
@@ -166,10 +166,17 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     }
     if (wave.empty()) { if (next < todo.size()) continue; break; }
     const int nb = (int)wave.size();
-    const bool allow_fast = ctx->kernel_version != 1;
-    std::stable_partition(wave.begin(), wave.end(), [&](int i) { return allow_fast && models[jobs[i].model].fast.ok != 0; });
-    int nfast = 0;
-    for (int i : wave) if (allow_fast && models[jobs[i].model].fast.ok != 0) ++nfast;
+    // kernel class per block: 0 = skewed-pipeline encoder (zpq_kernels3.cu), 1 = fast sequential kernel
+    // (zpq_kernels2.cu; always used for decoding), 2 = generic kernel (zpq_kernels.cu)
+    auto kclass = [&](int i) -> int {
+      const ZModel& Mi = models[jobs[i].model];
+      if (ctx->kernel_version == 1) return 2;
+      if (!decode && ctx->kernel_version != 2 && Mi.pipe.ok) return 0;
+      return Mi.fast.ok ? 1 : 2;
+    };
+    std::stable_sort(wave.begin(), wave.end(), [&](int a, int b) { return kclass(a) < kclass(b); });
+    int ncls[3] = {0, 0, 0};
+    for (int i : wave) ++ncls[kclass(i)];
 
     std::vector<ZBlock> blocks(nb);
     std::vector<uint64_t> seg_len;
@@ -246,23 +253,24 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     CK(zpq_launch_init(&A, nb, st), "zpq_init_kernel launch");
     CK(cudaEventRecord(ev[2], st), "event");
     {
-      // fast kernel for the models whose plan fits it (one CTA per SM, W warps sharing the 227 KB
-      // carve-out), generic kernel for the rest; the wave was ordered fast-first above
-      if (nfast > 0) {
-        uint32_t pw = 16;
-        for (int k = 0; k < nfast; ++k) pw = std::max(pw, models[jobs[wave[k]].model].fast.pw_bytes);
-        const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, (ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem()) / pw));
-        ZKernelArgs A1 = A;
-        A1.nblk = nfast;
-        CK(zpq_launch_code2(&A1, nfast, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
+      int first = 0;
+      for (int cls = 0; cls < 3; ++cls) {
+        const int cnt = ncls[cls];
+        if (cnt == 0) continue;
+        ZKernelArgs Ak = A;
+        Ak.blocks = A.blocks + first; Ak.status = A.status + first; Ak.out_len = A.out_len + first;
+        Ak.counter = A.counter + cls; Ak.nblk = cnt;
+        if (cls == 2) CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
+        else {
+          // one CTA per SM; W warps (blocks in flight) share the 227 KB carve-out
+          uint32_t pw = 16;
+          for (int k = first; k < first + cnt; ++k) pw = std::max(pw, models[jobs[wave[k]].model].fast.pw_bytes);
+          const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, (ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem()) / pw));
+          if (cls == 0) CK(zpq_launch_enc3(&Ak, cnt, ctx->sm_count, warps, (int)pw, st), "zpq_enc_kernel3 launch");
+          else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
+        }
         ++ctx->launches;
-      }
-      if (nb > nfast) {
-        ZKernelArgs A2 = A;
-        A2.blocks = A.blocks + nfast; A2.status = A.status + nfast; A2.out_len = A.out_len + nfast;
-        A2.counter = A.counter + 1; A2.nblk = nb - nfast;
-        CK(zpq_launch_code(&A2, nb - nfast, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
-        ++ctx->launches;
+        first += cnt;
       }
     }
     CK(cudaEventRecord(ev[3], st), "event");
@@ -374,7 +382,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return ZPQ_E_CUDA; }
   zpq_ctx* ctx = new zpq_ctx();
   ctx->device = device;
-  if (const char* kv = getenv("ZPQ_KERNEL")) ctx->kernel_version = atoi(kv) == 1 ? 1 : 2;
+  if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 3) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;

@@ -101,6 +101,23 @@ struct ZRecipes {
   uint32_t ops[ZPQ_RCP_MAX][32];
 };
 
+// Skewed-pipeline ENCODE plan.  While compressing, the coded bit is input data,
+// so no component depends on a later one or on the coder: the COMP chain is a
+// feed-forward pipeline.  Lane i runs `depth[i]` BYTES behind the head of the
+// stream; values cross lanes only through per-lane delay rings, never through
+// a same-bit dependency chain.
+#define ZPQ_PIPE_STEPS 8
+struct ZPipe {
+  uint32_t ok;
+  uint32_t dmax;                          // deepest stage, in bytes (<= 15)
+  uint32_t nsp;                           // special steps: MIX / MIX2 / SSE / AVG in component order
+  uint32_t sd[ZPQ_PIPE_STEPS];            // ZSTEP_PACK words (same layout as ZFast.sd)
+  uint32_t delay[ZPQ_MAX_LANES];          // 4 bits per special step: depth[owner] - depth[lane] for feeding lanes
+  uint8_t depth[ZPQ_MAX_LANES];
+  uint8_t dist_byte[ZPQ_MAX_LANES];       // byte value watched by the lane's ZS_DIST op (if has_dist)
+  uint8_t has_dist[ZPQ_MAX_LANES];
+};
+
 struct ZModel {
   uint32_t n, hh, hm;
   uint32_t prog_off;      // offset of the guarded program image in the program pool
@@ -114,6 +131,8 @@ struct ZModel {
   ZFill fills[ZPQ_MAX_FILLS];
   // ---- fast kernel plan (zpq_kernels2.cu) ----
   ZFast fast;
+  // ---- skewed-pipeline encode plan (zpq_kernels3.cu) ----
+  ZPipe pipe;
   ZRecipes rcp;
 };
 

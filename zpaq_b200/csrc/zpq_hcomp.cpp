@@ -207,7 +207,8 @@ bool parse(const uint8_t* prog, int len, int ncomp, LaneRcp lanes[32], ZRecipes*
       if (!lane_ok(base)) return false;
       c.i += 5;
       LaneRcp cur;
-      if (lanes[base].start == ZB_ZERO) cur = lanes[base];          // pure function of recent bytes: inline it
+      const bool pure = lanes[base].start == ZB_ZERO;
+      if (pure) cur = lanes[base];                                  // pure function of recent bytes: inline it
       else { cur.start = ZB_LANE; cur.base = base; cur.round = lanes[base].round + 1; }
       int d = base + 1, boff = 0;
       for (;;) {
@@ -221,7 +222,11 @@ bool parse(const uint8_t* prog, int len, int ncomp, LaneRcp lanes[32], ZRecipes*
         ++c.i;
         if (!lane_ok(d)) return false;
         lanes[d] = cur; lanes[d].written = true;
-        if (c.at(0, D_INC)) { ++d; ++c.i; continue; }
+        if (c.at(0, D_INC)) {
+          // a chain seeded by a stateful hash continues from the previous LINK (one pipeline stage back)
+          if (!pure) { cur = LaneRcp(); cur.start = ZB_LANE; cur.base = d; cur.round = lanes[d].round + 1; }
+          ++d; ++c.i; continue;
+        }
         break;
       }
       continue;

@@ -362,6 +362,70 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
   // (3) lane-parallel HCOMP recipes (zpq_hcomp.cpp)
   build_recipes(M, hdr + pos, prog_len);
   if (M->rcp.ok) for (uint32_t l = 0; l < M->n; ++l) if (M->rcp.len[l] > ZPQ_FAST_RCP) M->fast.ok = 0;
+
+  // ================= skewed-pipeline encode plan (zpq_kernels3.cu) =================
+  {
+    ZPipe& P = M->pipe;
+    memset(&P, 0, sizeof(P));
+    bool ok = M->fast.ok && M->rcp.ok && M->hm == 16;   // hm 16: byte offsets below 64 KiB never wrap the M ring
+    int dmax = 0, nsp = 0;
+    int owner_of[ZPQ_PIPE_STEPS];
+    const uint8_t* q = hdr + 7;
+    for (int i = 0; i < n && ok; ++i) {
+      int d = 0;
+      uint32_t word = 0;
+      switch (q[0]) {
+        case ZT_ISSE: d = P.depth[q[2]] + 1; break;
+        case ZT_SSE: d = P.depth[q[2]] + 1; word = ZSTEP_PACK(ZK_SSE, i, q[2], 0, 0, 0); break;
+        case ZT_AVG: d = std::max(P.depth[q[1]], P.depth[q[2]]) + 1; word = ZSTEP_PACK(ZK_AVG, i, q[1], q[2], q[3], 0); break;
+        case ZT_MIX2: d = std::max(P.depth[q[2]], P.depth[q[3]]) + 1; word = ZSTEP_PACK(ZK_MIX2, i, q[2], q[3], 0, 0); break;
+        case ZT_MIX:
+          for (int j = 0; j < q[3]; ++j) d = std::max<int>(d, P.depth[q[2] + j] + 1);
+          word = ZSTEP_PACK(ZK_MIX, i, q[2], q[3], q[4], 0);
+          break;
+        default: break;
+      }
+      P.depth[i] = (uint8_t)d;
+      dmax = std::max(dmax, d);
+      if (word) {
+        if (nsp >= ZPQ_PIPE_STEPS) { ok = false; break; }
+        owner_of[nsp] = i;
+        P.sd[nsp++] = word;
+      }
+      q += kCompLen[q[0]];
+    }
+    if (dmax > 15) ok = false;
+    if (ok) {
+      // slot numbers of MIX / SSE steps (register slots in the kernel), delays of feeding lanes
+      int nm = 0, nss = 0;
+      for (int s = 0; s < nsp; ++s) {
+        const uint32_t kind = P.sd[s] & 7u;
+        const int o = owner_of[s];
+        const int j = (int)((P.sd[s] >> 8) & 31u), k = (int)((P.sd[s] >> 13) & 63u);
+        if (kind == ZK_MIX) { P.sd[s] |= (uint32_t)nm++ << 27; for (int l = 0; l < k; ++l) P.delay[j + l] |= (uint32_t)(P.depth[o] - P.depth[j + l]) << (4 * s); }
+        else if (kind == ZK_SSE) { P.sd[s] |= (uint32_t)nss++ << 27; P.delay[j] |= (uint32_t)(P.depth[o] - P.depth[j]) << (4 * s); }
+        else {
+          // two inputs; if both are the same lane they share one delay
+          P.delay[j] |= (uint32_t)(P.depth[o] - P.depth[j]) << (4 * s);
+          if (k != j) P.delay[k] |= (uint32_t)(P.depth[o] - P.depth[k]) << (4 * s);
+        }
+      }
+      // recipe constraints of the skewed evaluation: a hash seeded by another lane must sit exactly one
+      // stage behind it, word-model groups likewise; at most one distance source per lane
+      const ZRecipes& R = M->rcp;
+      for (int l = 0; l < n && ok; ++l) {
+        if (R.start[l] == ZB_LANE && P.depth[l] != P.depth[R.base[l]] + 1) ok = false;
+        int ndist = 0;
+        for (int t = 0; t < R.len[l]; ++t) {
+          const uint32_t w = R.ops[t][l];
+          if ((w & 15u) == ZR_WORD) { if (!((R.ops[t + 1][l] >> 8) & 1u) && (l == 0 || P.depth[l] != P.depth[l - 1] + 1)) ok = false; ++t; continue; }
+          if (((w >> 4) & 15u) == ZS_DIST) { ++ndist; P.has_dist[l] = 1; P.dist_byte[l] = (uint8_t)((w >> 8) & 255u); }
+        }
+        if (ndist > 1) ok = false;
+      }
+    }
+    P.dmax = dmax; P.nsp = nsp; P.ok = ok ? 1 : 0;
+  }
   return ZPQ_OK;
 }
 
