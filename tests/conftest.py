@@ -27,15 +27,15 @@ def _make_ctx(kernel):
 
 @pytest.fixture(scope="session")
 def ctx():
-    """Production configuration: skewed-pipeline encoder + fast sequential decoder."""
-    c = _make_ctx("3")
+    """Production configuration: three-warp team encoder + fast sequential decoder."""
+    c = _make_ctx("4")
     yield c
     c.close()
 
 
-@pytest.fixture(scope="session", params=["3", "2", "1"], ids=["pipeline", "fast", "generic"])
+@pytest.fixture(scope="session", params=["4", "3", "2", "1"], ids=["team", "pipeline", "fast", "generic"])
 def kctx(request):
-    """Every kernel tier: 3 = production, 2 = fast sequential kernel for both directions, 1 = generic kernel."""
+    """Every kernel tier: 4 = production, 3 = one-warp pipeline encoder, 2 = fast sequential kernel for both directions, 1 = generic kernel."""
     c = _make_ctx(request.param)
     yield c
     c.close()

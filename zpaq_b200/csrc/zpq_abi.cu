@@ -64,7 +64,7 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   uint64_t launches = 0;
-  int kernel_version = 3;      // ZPQ_KERNEL=1: generic kernel only; 2: no skewed-pipeline encoder (A/B testing)
+  int kernel_version = 4;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team encoder
 };
 
 namespace {
@@ -166,16 +166,19 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     }
     if (wave.empty()) { if (next < todo.size()) continue; break; }
     const int nb = (int)wave.size();
-    // kernel class per block: 0 = skewed-pipeline encoder (zpq_kernels3.cu), 1 = fast sequential kernel
-    // (zpq_kernels2.cu; always used for decoding), 2 = generic kernel (zpq_kernels.cu)
+    // kernel class per block: 0 = three-warp team encoder (zpq_kernels4.cu), 1 = one-warp skewed-pipeline
+    // encoder (zpq_kernels3.cu), 2 = fast sequential kernel (zpq_kernels2.cu; always used for decoding),
+    // 3 = generic kernel (zpq_kernels.cu).  ZPQ_KERNEL caps the tier (A/B testing).
+    const int kv = ctx->kernel_version;
     auto kclass = [&](int i) -> int {
       const ZModel& Mi = models[jobs[i].model];
-      if (ctx->kernel_version == 1) return 2;
-      if (!decode && ctx->kernel_version != 2 && Mi.pipe.ok) return 0;
-      return Mi.fast.ok ? 1 : 2;
+      if (kv == 1) return 3;
+      if (!decode && kv >= 4 && Mi.team.ok) return 0;
+      if (!decode && kv >= 3 && Mi.pipe.ok) return 1;
+      return Mi.fast.ok ? 2 : 3;
     };
     std::stable_sort(wave.begin(), wave.end(), [&](int a, int b) { return kclass(a) < kclass(b); });
-    int ncls[3] = {0, 0, 0};
+    int ncls[4] = {0, 0, 0, 0};
     for (int i : wave) ++ncls[kclass(i)];
 
     std::vector<ZBlock> blocks(nb);
@@ -254,20 +257,26 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     CK(cudaEventRecord(ev[2], st), "event");
     {
       int first = 0;
-      for (int cls = 0; cls < 3; ++cls) {
+      for (int cls = 0; cls < 4; ++cls) {
         const int cnt = ncls[cls];
         if (cnt == 0) continue;
         ZKernelArgs Ak = A;
         Ak.blocks = A.blocks + first; Ak.status = A.status + first; Ak.out_len = A.out_len + first;
         Ak.counter = A.counter + cls; Ak.nblk = cnt;
-        if (cls == 2) CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
+        if (cls == 3) CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
         else {
-          // one CTA per SM; W warps (blocks in flight) share the 227 KB carve-out
+          // one CTA per SM; W blocks in flight share the 227 KB carve-out
           uint32_t pw = 16;
           for (int k = first; k < first + cnt; ++k) pw = std::max(pw, models[jobs[wave[k]].model].fast.pw_bytes);
-          const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, (ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem()) / pw));
-          if (cls == 0) CK(zpq_launch_enc3(&Ak, cnt, ctx->sm_count, warps, (int)pw, st), "zpq_enc_kernel3 launch");
-          else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
+          const uint64_t room = ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem();
+          if (cls == 0) {
+            const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room / (pw + 16)));
+            CK(zpq_launch_enc4(&Ak, cnt, ctx->sm_count, teams, (int)pw, st), "zpq_enc_kernel4 launch");
+          } else {
+            const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, room / pw));
+            if (cls == 1) CK(zpq_launch_enc3(&Ak, cnt, ctx->sm_count, warps, (int)pw, st), "zpq_enc_kernel3 launch");
+            else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
+          }
         }
         ++ctx->launches;
         first += cnt;
@@ -382,7 +391,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return ZPQ_E_CUDA; }
   zpq_ctx* ctx = new zpq_ctx();
   ctx->device = device;
-  if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 3) ctx->kernel_version = v; }
+  if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 4) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;

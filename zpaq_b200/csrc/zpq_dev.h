@@ -118,6 +118,28 @@ struct ZPipe {
   uint8_t has_dist[ZPQ_MAX_LANES];
 };
 
+// Team plan (zpq_kernels4.cu): the skewed pipeline of ZPipe split over THREE warps per block so that
+// the block's instruction stream is issued by three schedulers at once:
+//   role 0 = every ICM / ISSE component (one code path, no divergence)
+//   role 1 = every MIX component (lane l = input l, cooperative dot product)
+//   role 2 = everything else (CM, MATCH, CONST, AVG, MIX2, SSE)
+// The arithmetic coder rides with the role that owns the last component.  Predictions cross
+// roles (and lanes) through per-component rings of 32 byte-slots x 8 x int16 in the block's arena.
+#define ZPQ_ROLES 3
+struct ZTeam {
+  uint32_t ok;
+  uint32_t coder_role;
+  uint32_t pmask[ZPQ_ROLES];             // roles this role reads predictions from
+  uint32_t cmask[ZPQ_ROLES];             // roles that read this role's predictions
+  uint32_t nmix;
+  uint32_t mix_comp[ZPQ_FAST_MIX];
+  uint32_t nsse;
+  uint32_t sse_comp[ZPQ_FAST_SSE];
+  uint32_t ring_off16;                   // arena offset of the rings (n x 512 B)
+  uint8_t role_of[ZPQ_MAX_LANES];        // component -> role
+  uint8_t comp_at[ZPQ_ROLES][32];        // role 0 / 2: lane -> component (0xff: idle lane)
+};
+
 struct ZModel {
   uint32_t n, hh, hm;
   uint32_t prog_off;      // offset of the guarded program image in the program pool
@@ -133,6 +155,8 @@ struct ZModel {
   ZFast fast;
   // ---- skewed-pipeline encode plan (zpq_kernels3.cu) ----
   ZPipe pipe;
+  // ---- three-warp team plan (zpq_kernels4.cu) ----
+  ZTeam team;
   ZRecipes rcp;
 };
 

@@ -297,6 +297,7 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
     M->fills[nf].kind = ZF_ZERO; M->fills[nf].value = 0; ++nf;
   }
   M->nfills = nf;
+  const uint32_t ring_off16 = lay.alloc((uint64_t)n * 512);   // prediction rings of the team kernel (never needs init)
   if (lay.pos16 >= ((uint64_t)1 << 32)) return fail(err, ZPQ_E_NOMEM, "Out of memory");
   M->arena_bytes = ((lay.pos16 * 16) + 255) & ~(uint64_t)255;
 
@@ -425,6 +426,51 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
       }
     }
     P.dmax = dmax; P.nsp = nsp; P.ok = ok ? 1 : 0;
+  }
+
+  // ================= three-warp team plan (zpq_kernels4.cu) =================
+  {
+    ZTeam& T = M->team;
+    memset(&T, 0, sizeof(T));
+    memset(T.comp_at, 0xff, sizeof(T.comp_at));
+    T.ring_off16 = ring_off16;
+    bool ok = M->pipe.ok != 0;
+    int fill[ZPQ_ROLES] = {0, 0, 0};
+    const uint8_t* q = hdr + 7;
+    for (int i = 0; i < n && ok; ++i) {
+      int role = 2;
+      if (q[0] == ZT_ICM || q[0] == ZT_ISSE) role = 0;
+      else if (q[0] == ZT_MIX) role = 1;
+      T.role_of[i] = (uint8_t)role;
+      if (role == 1) { if (T.nmix >= ZPQ_FAST_MIX) ok = false; else T.mix_comp[T.nmix++] = i; }
+      else { if (fill[role] >= 32) ok = false; else T.comp_at[role][fill[role]++] = (uint8_t)i; }
+      if (q[0] == ZT_SSE) { if (T.nsse >= ZPQ_FAST_SSE) ok = false; else T.sse_comp[T.nsse++] = i; }
+      // producer / consumer relations between roles
+      auto link = [&](int j) { const int rj = T.role_of[j]; if (rj != role) { T.pmask[role] |= 1u << rj; T.cmask[rj] |= 1u << role; } };
+      switch (q[0]) {
+        case ZT_ISSE: case ZT_SSE: link(q[2]); break;
+        case ZT_AVG: link(q[1]); link(q[2]); break;
+        case ZT_MIX2: link(q[2]); link(q[3]); break;
+        case ZT_MIX: for (int j = 0; j < q[3]; ++j) link(q[2] + j); break;
+        default: break;
+      }
+      q += kCompLen[q[0]];
+    }
+    T.coder_role = T.role_of[n - 1];
+    // recipe sources must live in the same warp as their consumer; mixer contexts must be pure folds
+    for (int l = 0; l < n && ok; ++l) {
+      const ZRecipes& R = M->rcp;
+      if (R.start[l] == ZB_LANE && T.role_of[R.base[l]] != T.role_of[l]) ok = false;
+      if (T.role_of[l] == 1 && R.start[l] != ZB_ZERO) ok = false;
+      for (int t = 0; t < R.len[l]; ++t)
+        if ((R.ops[t][l] & 15u) == ZR_WORD) {
+          if (!((R.ops[t + 1][l] >> 8) & 1u) && (l == 0 || T.role_of[l - 1] != T.role_of[l])) ok = false;
+          if (T.role_of[l] == 1) ok = false;
+          ++t;
+        }
+        else if (T.role_of[l] == 1 && ((R.ops[t][l] >> 4) & 15u) == ZS_DIST) ok = false;
+    }
+    T.ok = ok ? 1 : 0;
   }
   return ZPQ_OK;
 }
