@@ -27,15 +27,15 @@ def _make_ctx(kernel):
 
 @pytest.fixture(scope="session")
 def ctx():
-    """Production configuration: three-warp team encoder + fast sequential decoder."""
-    c = _make_ctx("4")
+    """Production configuration: wavefront encoder + fast sequential decoder."""
+    c = _make_ctx("5")
     yield c
     c.close()
 
 
-@pytest.fixture(scope="session", params=["4", "3", "2", "1"], ids=["team", "pipeline", "fast", "generic"])
+@pytest.fixture(scope="session", params=["5", "4", "3", "2", "1"], ids=["wave", "team", "pipeline", "fast", "generic"])
 def kctx(request):
-    """Every kernel tier: 4 = production, 3 = one-warp pipeline encoder, 2 = fast sequential kernel for both directions, 1 = generic kernel."""
+    """Every kernel tier: 5 = production (wavefront encoder), 4 = team encoder, 3 = one-warp pipeline encoder, 2 = fast sequential kernel for both directions, 1 = generic kernel."""
     c = _make_ctx(request.param)
     yield c
     c.close()

@@ -59,12 +59,12 @@ struct zpq_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   ZTables* d_tables = nullptr;
   void* ws = nullptr; uint64_t ws_bytes = 0; bool own_ws = true;
-  DevBuf d_in, d_out, d_meta;
+  DevBuf d_in, d_out, d_meta, d_pbuf, d_cstate;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   float ms[3] = {0, 0, 0};
   uint64_t launches = 0;
-  int kernel_version = 4;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team encoder
+  int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
 };
 
 namespace {
@@ -135,7 +135,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot), "cudaMemGetInfo");
     const uint64_t avail = (uint64_t)fr + ctx->ws_bytes;
-    const uint64_t reserve = (uint64_t)3 << 30;     // staging buffers, CUDA context
+    const uint64_t reserve = ((uint64_t)3 << 30) + ((!decode && ctx->kernel_version >= 5) ? ((uint64_t)14 << 30) : 0);   // staging, CUDA context, prediction streams
     uint64_t want = std::min(need_all, avail > reserve ? avail - reserve : 0);
     if (want > ctx->ws_bytes) {
       if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
@@ -166,19 +166,25 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     }
     if (wave.empty()) { if (next < todo.size()) continue; break; }
     const int nb = (int)wave.size();
-    // kernel class per block: 0 = three-warp team encoder (zpq_kernels4.cu), 1 = one-warp skewed-pipeline
-    // encoder (zpq_kernels3.cu), 2 = fast sequential kernel (zpq_kernels2.cu; always used for decoding),
-    // 3 = generic kernel (zpq_kernels.cu).  ZPQ_KERNEL caps the tier (A/B testing).
+    // kernel class per block: 0 = wavefront encoder (zpq_kernels5.cu), 1 = three-warp team encoder
+    // (zpq_kernels4.cu), 2 = one-warp skewed-pipeline encoder (zpq_kernels3.cu), 3 = fast sequential kernel
+    // (zpq_kernels2.cu; always used for decoding), 4 = generic kernel (zpq_kernels.cu).
+    // ZPQ_KERNEL caps the tier (A/B testing).
     const int kv = ctx->kernel_version;
     auto kclass = [&](int i) -> int {
       const ZModel& Mi = models[jobs[i].model];
-      if (kv == 1) return 3;
-      if (!decode && kv >= 4 && Mi.team.ok) return 0;
-      if (!decode && kv >= 3 && Mi.pipe.ok) return 1;
-      return Mi.fast.ok ? 2 : 3;
+      if (kv == 1) return 4;
+      if (!decode && kv >= 5 && Mi.wave.ok) return 0;
+      if (!decode && kv >= 4 && Mi.team.ok) return 1;
+      if (!decode && kv >= 3 && Mi.pipe.ok) return 2;
+      return Mi.fast.ok ? 3 : 4;
     };
-    std::stable_sort(wave.begin(), wave.end(), [&](int a, int b) { return kclass(a) < kclass(b); });
-    int ncls[4] = {0, 0, 0, 0};
+    // class first, then model: the wavefront encoder wants 32 blocks of one model per warp
+    std::stable_sort(wave.begin(), wave.end(), [&](int a, int b) {
+      const int ca = kclass(a), cb = kclass(b);
+      return ca != cb ? ca < cb : jobs[a].model < jobs[b].model;
+    });
+    int ncls[5] = {0, 0, 0, 0, 0};
     for (int i : wave) ++ncls[kclass(i)];
 
     std::vector<ZBlock> blocks(nb);
@@ -257,28 +263,70 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     CK(cudaEventRecord(ev[2], st), "event");
     {
       int first = 0;
-      for (int cls = 0; cls < 4; ++cls) {
+      for (int cls = 0; cls < 5; ++cls) {
         const int cnt = ncls[cls];
         if (cnt == 0) continue;
         ZKernelArgs Ak = A;
         Ak.blocks = A.blocks + first; Ak.status = A.status + first; Ak.out_len = A.out_len + first;
         Ak.counter = A.counter + cls; Ak.nblk = cnt;
-        if (cls == 3) CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch");
+        if (cls == 4) { CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch"); ++ctx->launches; }
+        else if (cls == 0) {
+          // ---- wavefront encoder: groups of <= 32 blocks of one model, one launch per wave ----
+          std::vector<uint32_t> gfirst, gcount, bgroup(cnt), blane(cnt);
+          int ncs = 2; uint64_t maxN = 0; uint32_t dmaxc = 0;
+          for (int k = 0; k < cnt; ++k) {
+            const IJob& J = jobs[wave[first + k]];
+            if (k == 0 || J.model != jobs[wave[first + k - 1]].model || gcount.back() == 32) { gfirst.push_back((uint32_t)k); gcount.push_back(0); }
+            bgroup[k] = (uint32_t)gfirst.size() - 1; blane[k] = gcount.back()++;
+            ncs = std::max(ncs, (int)models[J.model].n + 1);
+            maxN = std::max(maxN, J.in_total);
+            dmaxc = std::max(dmaxc, models[J.model].wave.dcoder);
+          }
+          const int ngroups = (int)gfirst.size();
+          int CB = 2048;
+          size_t fr = 0, tot = 0;
+          CK(cudaMemGetInfo(&fr, &tot), "cudaMemGetInfo");
+          while (CB > 128 && (uint64_t)ngroups * ncs * 16 * CB * 512 > (uint64_t)fr + ctx->d_pbuf.cap - ((uint64_t)1 << 30)) CB >>= 1;
+          const uint64_t pbytes = (uint64_t)ngroups * ncs * 16 * CB * 512, cbytes = (uint64_t)cnt * ncs * 64;
+          CK(ctx->d_pbuf.reserve(pbytes), "prediction stream cudaMalloc");
+          CK(ctx->d_cstate.reserve(cbytes + (uint64_t)(ngroups * 2 + cnt * 2) * 4 + 1024), "wave state cudaMalloc");
+          uint8_t* dc = (uint8_t*)ctx->d_cstate.p;
+          uint32_t* d_gfirst = (uint32_t*)(dc + align_up(cbytes, 256));
+          uint32_t* d_gcount = d_gfirst + ngroups;
+          uint32_t* d_bgroup = d_gcount + ngroups;
+          uint32_t* d_blane = d_bgroup + cnt;
+          CK(cudaMemsetAsync(dc, 0, cbytes, st), "memset wave state");
+          CK(cudaMemcpyAsync(d_gfirst, gfirst.data(), (size_t)ngroups * 4, cudaMemcpyHostToDevice, st), "H2D groups");
+          CK(cudaMemcpyAsync(d_gcount, gcount.data(), (size_t)ngroups * 4, cudaMemcpyHostToDevice, st), "H2D groups");
+          CK(cudaMemcpyAsync(d_bgroup, bgroup.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, st), "H2D groups");
+          CK(cudaMemcpyAsync(d_blane, blane.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, st), "H2D groups");
+          CK(cudaStreamSynchronize(st), "sync");     // host vectors above go out of scope
+          ZWaveArgs Wv;
+          Wv.A = Ak; Wv.pbuf = (uint4*)ctx->d_pbuf.p; Wv.cstate = (uint32_t*)dc;
+          Wv.group_first = d_gfirst; Wv.group_count = d_gcount; Wv.blk_group = d_bgroup; Wv.blk_lane = d_blane;
+          Wv.chunk_bytes = CB; Wv.ncs = ncs; Wv.ngroups = ngroups;
+          const int nwaves = (int)((maxN + CB - 1) / CB) + (int)dmaxc + 1;
+          for (int w = 0; w < std::max(nwaves, (int)dmaxc + 1); ++w) {
+            Wv.wave = w;
+            CK(zpq_launch_wave(&Wv, st), "zpq_wave_kernel launch");
+            ++ctx->launches;
+          }
+        }
         else {
           // one CTA per SM; W blocks in flight share the 227 KB carve-out
           uint32_t pw = 16;
           for (int k = first; k < first + cnt; ++k) pw = std::max(pw, models[jobs[wave[k]].model].fast.pw_bytes);
           const uint64_t room = ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem();
-          if (cls == 0) {
+          if (cls == 1) {
             const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room / (pw + 16)));
             CK(zpq_launch_enc4(&Ak, cnt, ctx->sm_count, teams, (int)pw, st), "zpq_enc_kernel4 launch");
           } else {
             const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, room / pw));
-            if (cls == 1) CK(zpq_launch_enc3(&Ak, cnt, ctx->sm_count, warps, (int)pw, st), "zpq_enc_kernel3 launch");
+            if (cls == 2) CK(zpq_launch_enc3(&Ak, cnt, ctx->sm_count, warps, (int)pw, st), "zpq_enc_kernel3 launch");
             else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
           }
+          ++ctx->launches;
         }
-        ++ctx->launches;
         first += cnt;
       }
     }
@@ -391,7 +439,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return ZPQ_E_CUDA; }
   zpq_ctx* ctx = new zpq_ctx();
   ctx->device = device;
-  if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 4) ctx->kernel_version = v; }
+  if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -411,7 +459,7 @@ void zpq_destroy(zpq_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release();
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release();
   if (ctx->own_ws && ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

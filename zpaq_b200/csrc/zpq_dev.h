@@ -118,6 +118,19 @@ struct ZPipe {
   uint8_t has_dist[ZPQ_MAX_LANES];
 };
 
+// Wavefront encode plan (zpq_kernels5.cu): one THREAD per (block, component); a component at depth d
+// codes chunk w-d in wave w.  Context recipes are flattened so that every thread is self-contained:
+// a hash seeded by another component carries a private copy of that component's state.
+#define ZPQ_FLAT_MAX 40
+#define ZPQ_FLAT_SEGS 4
+#define ZR_SEG 8                 // op word: ZR_SEG | start<<4 ; begins the next segment of a flattened recipe
+struct ZWave {
+  uint32_t ok;
+  uint32_t dcoder;                         // depth of the coder stage = depth[n-1] + 1
+  uint32_t flat_len[ZPQ_MAX_LANES];
+  uint32_t flat[ZPQ_MAX_LANES][ZPQ_FLAT_MAX];
+};
+
 // Team plan (zpq_kernels4.cu): the skewed pipeline of ZPipe split over THREE warps per block so that
 // the block's instruction stream is issued by three schedulers at once:
 //   role 0 = every ICM / ISSE component (one code path, no divergence)
@@ -157,6 +170,8 @@ struct ZModel {
   ZPipe pipe;
   // ---- three-warp team plan (zpq_kernels4.cu) ----
   ZTeam team;
+  // ---- wavefront encode plan (zpq_kernels5.cu) ----
+  ZWave wave;
   ZRecipes rcp;
 };
 
@@ -195,6 +210,19 @@ struct ZKernelArgs {
   unsigned int* counter;
   const ZTables* tables;
   int nblk;
+};
+
+
+// Arguments of the wavefront encode kernel (zpq_kernels5.cu), one launch per wave.
+struct ZWaveArgs {
+  ZKernelArgs A;                 // blocks of this launch class, grouped: 32 consecutive blocks of one model = a group
+  uint4* pbuf;                   // prediction streams [group][component slot][16 chunk slots][chunk byte][lane]
+  uint32_t* cstate;              // [block][component slot][16 words] state carried between waves (zeroed per batch)
+  const uint32_t* group_first;   // first block index of each group
+  const uint32_t* group_count;   // blocks in the group (<= 32)
+  const uint32_t* blk_group;     // block -> group
+  const uint32_t* blk_lane;      // block -> lane inside its group
+  int wave, chunk_bytes, ncs, ngroups;   // ncs = component slots per block = max components + 1 (coder)
 };
 
 #endif

@@ -324,4 +324,107 @@ void build_recipes(ZModel* M, const uint8_t* prog, int prog_len) {
   R = tmp;
 }
 
+
+// ---------------------------------------------------------------------------
+// Flattened recipes for the wavefront encoder: component l's op list is prefixed with the lists of
+// the components its hash is seeded from (ZB_LANE bases, earlier lanes of its word-model group), each
+// as a segment with its own private state.  Verified against the per-lane recipes on a byte stream.
+namespace {
+struct FlatEval {
+  uint32_t st[ZPQ_FLAT_SEGS];
+  uint32_t dist_last; uint32_t c; uint64_t hist;
+  std::vector<uint8_t> in;
+  FlatEval() { memset(st, 0, sizeof(st)); dist_last = 0; c = 0; hist = 0; }
+  uint32_t step(const uint32_t* ops, uint32_t len, uint32_t byte, uint32_t dist_byte) {
+    --c; in.push_back((uint8_t)byte);
+    const long long bpos = (long long)in.size() - 1;
+    hist = (hist << 8) | byte;
+    if (byte == dist_byte) dist_last = c;
+    int k = -1; uint32_t acc = 0, prev_new = 0, prev_old = 0;
+    for (uint32_t t = 0; t < len; ++t) {
+      const uint32_t w = ops[t];
+      const uint32_t op = w & 15, src = (w >> 4) & 15, arg = (w >> 8) & 255, off = w >> 16;
+      if (op == ZR_SEG) {
+        if (k >= 0) { prev_old = st[k]; st[k] = acc; prev_new = acc; }
+        ++k;
+        acc = src == ZB_ZERO ? 0 : (src == ZB_OWN ? st[k] : prev_new);
+        continue;
+      }
+      uint32_t x = 0;
+      if (src == ZS_BYTE) x = off < 8 ? ((uint32_t)(hist >> (8 * off)) & arg) : ((long long)off <= bpos ? (in[bpos - off] & arg) : 0);
+      else if (src == ZS_POSAND) x = c & arg;
+      else if (src == ZS_POSMOD) x = arg ? c % arg : 0;
+      else if (src == ZS_DIST) { x = dist_last - c; if (x > 255) x = 255; }
+      switch (op) {
+        case ZR_FOLD: acc = (acc + x + 512) * 773; break;
+        case ZR_SHL8ADD: acc = (acc << 8) + x; break;
+        case ZR_SHR: acc >>= arg; break;
+        case ZR_SHL: acc <<= arg; break;
+        case ZR_ROLL: acc = acc * off + byte + 1; break;
+        case ZR_WORD: {
+          const uint32_t w2 = ops[t + 1];
+          const uint32_t v2 = off & 255, v3 = off >> 8, mult = w2 & 255, first = (w2 >> 8) & 1;
+          if ((((byte & arg) - v2) & 255) < v3) acc = acc * mult + byte + 1;
+          else acc = first ? 0 : prev_old;
+          ++t;
+          break;
+        }
+        default: break;
+      }
+    }
+    if (k >= 0) st[k] = acc;
+    return acc;
+  }
+};
+}  // namespace
+
+void build_wave_plan(ZModel* M) {
+  ZWave& W = M->wave;
+  memset(&W, 0, sizeof(W));
+  const ZRecipes& R = M->rcp;
+  if (!R.ok || !M->pipe.ok || M->hm != 16) return;
+  const int n = (int)M->n;
+  for (int l = 0; l < n; ++l) {
+    // chain of components whose state this hash needs, root first
+    std::vector<int> chain;
+    int cur = l;
+    for (;;) {
+      chain.insert(chain.begin(), cur);
+      if (R.start[cur] == ZB_LANE) { cur = R.base[cur]; continue; }
+      if (R.len[cur] >= 2 && (R.ops[0][cur] & 15u) == ZR_WORD && !((R.ops[1][cur] >> 8) & 1u) && cur > 0) { --cur; continue; }
+      break;
+    }
+    if ((int)chain.size() > ZPQ_FLAT_SEGS) return;
+    std::vector<uint32_t> f;
+    int ndist = 0;
+    for (size_t s = 0; s < chain.size(); ++s) {
+      const int c = chain[s];
+      f.push_back((uint32_t)ZR_SEG | (uint32_t)R.start[c] << 4);
+      for (int t = 0; t < R.len[c]; ++t) {
+        f.push_back(R.ops[t][c]);
+        if ((R.ops[t][c] & 15u) == ZR_WORD) { f.push_back(R.ops[t + 1][c]); ++t; }
+        else if (((R.ops[t][c] >> 4) & 15u) == ZS_DIST) ++ndist;
+      }
+    }
+    if (f.size() > ZPQ_FLAT_MAX || ndist > 1) return;
+    W.flat_len[l] = (uint32_t)f.size();
+    for (size_t t = 0; t < f.size(); ++t) W.flat[l][t] = f[t];
+  }
+  // self-check against the per-lane recipes
+  HostRcp rc(R, n, (int)M->hh, (int)M->hm);
+  std::vector<FlatEval> fe(n);
+  uint32_t s = 4242;
+  for (int i = 0; i < 4000; ++i) {
+    s = s * 1664525u + 1013904223u;
+    uint32_t byte = s >> 24;
+    if ((i / 400) & 1) byte = "the quick\nbrown fox jumps over\n"[(s >> 24) % 31];
+    rc.step(byte);
+    for (int l = 0; l < n; ++l)
+      if (fe[l].step(W.flat[l], W.flat_len[l], byte, M->pipe.dist_byte[l]) != rc.h[l]) return;
+  }
+  W.dcoder = M->pipe.depth[n - 1] + 1;
+  if (W.dcoder > 15) return;
+  W.ok = 1;
+}
+
 }  // namespace zpq

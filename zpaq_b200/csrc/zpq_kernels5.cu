@@ -1,0 +1,461 @@
+// zpq_kernels5.cu -- wavefront ENCODE for sm_100a: one thread per (block, component).
+//
+// Encoding is a feed-forward pipeline over components (zpq_kernels3.cu header): no component reads a
+// later component's output or the coder's state.  Here the pipeline is unrolled in TIME over kernel
+// launches instead of over lanes of one warp:
+//
+//   * the input of every block is cut into chunks of `chunk_bytes`; in wave w a component at pipeline
+//     depth d codes chunk w-d, the coder (depth of the last component + 1) codes chunk w-dc;
+//   * a thread owns ONE component of ONE block for one chunk: its tables are private, its state (context
+//     hashes, MATCH pointers, coder range) is kept in a 64-byte record between waves;
+//   * the 32 lanes of a warp are the same component of 32 different blocks with the same model, so the
+//     per-type code path is warp-uniform (no SIMT divergence), and the SM hides HBM/L2 latency by
+//     switching among ~18 resident warps instead of stalling one;
+//   * predictions travel through HBM streams (one 16-byte vector of eight int16 per component per
+//     byte, laid out [group][component][chunk slot][byte][lane] so that a warp reads and writes 512
+//     contiguous bytes); a stream written in wave w is read in waves w+1 .. w+15;
+//   * MIX components get a whole warp per block (lane = input, coalesced weight row, redux.sync);
+//   * kernel boundaries are the only synchronisation.
+//
+// Context hashes come from the flattened recipes of zpq_hcomp.cpp (build_wave_plan): each thread
+// carries private copies of the states its hash is seeded from.  Bit-exactness: every table and every
+// state word is touched by exactly one thread in stream order; tests compare this tier with the oracle.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "zpq_dev.h"
+#include "zpq_kernels.h"
+#include "zpq_kcommon.cuh"
+
+struct Enc5 {
+  u32 low, high;
+  u8* out; u64 out_pos, out_cap;
+  int status;
+};
+
+__device__ __forceinline__ void enc5_bit(Enc5& C, int y, u32 p16) {
+  const u32 mid = C.low + (u32)(((u64)(C.high - C.low) * p16) >> 16);
+  if (y) C.high = mid; else C.low = mid + 1;
+  while ((C.high ^ C.low) < 0x1000000u) {
+    if (C.out_pos < C.out_cap) C.out[C.out_pos] = (u8)(C.high >> 24);
+    else C.status = ST_FULL;
+    ++C.out_pos;
+    C.high = C.high << 8 | 255u;
+    C.low = C.low << 8;
+    C.low += (C.low == 0);
+  }
+}
+
+__device__ __forceinline__ int vget(const uint4& v, int bit) {
+  const u32 w = (bit & 4) ? ((bit & 2) ? v.w : v.z) : ((bit & 2) ? v.y : v.x);
+  return (int)(short)(w >> ((bit & 1) * 16));
+}
+__device__ __forceinline__ void vset(uint4& v, int bit, int p) {
+  const u32 sh = (bit & 1) * 16;
+  const u32 keep = ~(0xffffu << sh), val = ((u32)p & 0xffffu) << sh;
+  if (bit & 4) { if (bit & 2) v.w = (v.w & keep) | val; else v.z = (v.z & keep) | val; }
+  else         { if (bit & 2) v.y = (v.y & keep) | val; else v.x = (v.x & keep) | val; }
+}
+
+// Flattened recipe (zpq_hcomp.cpp: build_wave_plan / FlatEval).  st[] = private segment states.
+__device__ __forceinline__ u32 flat_eval(const u32* __restrict__ ops, u32 len, u32 st[ZPQ_FLAT_SEGS], u32 cur, u64 hs,
+                                         int bpos, const u8* in, u32 dist_last) {
+  const u32 vc = (u32)(-(bpos + 1));
+  int k = -1; u32 acc = 0, prev_new = 0, prev_old = 0;
+  for (u32 t = 0; t < len; ++t) {
+    const u32 w = __ldg(ops + t);
+    const u32 op = w & 15u, src = (w >> 4) & 15u, arg = (w >> 8) & 255u, off = w >> 16;
+    if (op == ZR_SEG) {
+      if (k >= 0) {
+        const u32 old = k == 0 ? st[0] : (k == 1 ? st[1] : (k == 2 ? st[2] : st[3]));
+        if (k == 0) st[0] = acc; else if (k == 1) st[1] = acc; else if (k == 2) st[2] = acc; else st[3] = acc;
+        prev_old = old; prev_new = acc;
+      }
+      ++k;
+      const u32 own = k == 0 ? st[0] : (k == 1 ? st[1] : (k == 2 ? st[2] : st[3]));
+      acc = src == ZB_ZERO ? 0u : (src == ZB_OWN ? own : prev_new);
+      continue;
+    }
+    u32 x = 0;
+    if (src == ZS_BYTE) {
+      if (off < 8) x = (u32)(hs >> (off * 8)) & arg;
+      else x = ((int)off <= bpos) ? ((u32)in[bpos - (int)off] & arg) : 0u;
+    }
+    else if (src == ZS_POSAND) x = vc & arg;
+    else if (src == ZS_POSMOD) x = arg ? vc % arg : 0u;
+    else if (src == ZS_DIST) x = min(dist_last - vc, 255u);
+    if (op == ZR_FOLD) acc = (acc + x + 512u) * 773u;
+    else if (op == ZR_SHL8ADD) acc = (acc << 8) + x;
+    else if (op == ZR_SHR) acc >>= arg;
+    else if (op == ZR_SHL) acc <<= arg;
+    else if (op == ZR_ROLL) acc = acc * off + cur + 1u;
+    else if (op == ZR_WORD) {
+      const u32 w2 = __ldg(ops + t + 1);
+      const u32 v2 = off & 255u, v3 = off >> 8, mult = w2 & 255u, first = (w2 >> 8) & 1u;
+      if ((((cur & arg) - v2) & 255u) < v3) acc = acc * mult + cur + 1u;
+      else acc = first ? 0u : prev_old;
+      ++t;
+    }
+  }
+  if (k == 0) st[0] = acc; else if (k == 1) st[1] = acc; else if (k == 2) st[2] = acc; else if (k == 3) st[3] = acc;
+  return acc;
+}
+
+#define CS_WORDS 16     // per (block, component) state record, in u32
+
+__global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_tables(smem, W.A.tables);
+  __syncthreads();
+  const Tabs S = make_tabs(smem);
+  const ZKernelArgs& A = W.A;
+
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // global warp index
+  const int CB = W.chunk_bytes, NCS = W.ncs;
+  const int nA = W.ngroups * NCS;
+
+  if (gw < nA) {
+    // =======================================================================================
+    // thread = (block, component) ; warp = one component of the 32 blocks of a group
+    // =======================================================================================
+    const int g = gw / NCS, c = gw - g * NCS;
+    const int cnt = (int)W.group_count[g];
+    if (lane >= cnt) return;
+    const int bi = (int)W.group_first[g] + lane;
+    const ZBlock B = A.blocks[bi];
+    const ZModel* __restrict__ ZM = A.models + B.model;
+    const int n = (int)ZM->n;
+    u8* const arena = A.arena + B.arena_off;
+    int N = 0;
+    for (u32 sg = 0; sg < B.nseg; ++sg) N += (int)A.seg_len[B.seg_first + sg];
+    const u8* const in = A.in + B.in_off;
+    u32* const cs = W.cstate + ((size_t)bi * NCS + c) * CS_WORDS;
+    uint4* const pb = W.pbuf + (size_t)g * NCS * 16 * CB * 32;        // this group's streams
+#define PBIDX(comp, slot, i) ((((size_t)(comp) * 16 + (slot)) * CB + (i)) * 32 + lane)
+
+    if (c == NCS - 1) {
+      // ---------------- coder stage ----------------
+      const int ch = W.wave - (int)ZM->wave.dcoder;
+      if (ch < 0) return;
+      const int b0 = ch * CB;
+      if (b0 >= N && !(ch == 0)) return;
+      const int b1 = min(N, b0 + CB);
+      Enc5 C;
+      C.out = A.out + B.out_off; C.out_cap = B.out_cap;
+      u32 seg; u64 seg_end, seg_start_out;
+      if (ch == 0) {
+        C.low = 1; C.high = 0xffffffffu; C.out_pos = 0; C.status = ST_OK;
+        seg = 0; seg_end = B.nseg ? A.seg_len[B.seg_first] : 0; seg_start_out = 0;
+      } else {
+        C.low = cs[0]; C.high = cs[1]; C.out_pos = (u64)cs[2] | (u64)cs[3] << 32; C.status = (int)cs[9];
+        seg = cs[4]; seg_end = (u64)cs[5] | (u64)cs[6] << 32; seg_start_out = (u64)cs[7] | (u64)cs[8] << 32;
+      }
+      const int slot = ch & 15;
+      for (int pos = b0;; ++pos) {
+        // Compressor::endSegment: EOS after the last byte of a segment (libzpaq.cpp:2950-2952)
+        while (seg < B.nseg && seg_end == (u64)pos) {
+          enc5_bit(C, 1, 0);
+          A.seg_out[B.seg_first + seg] = C.out_pos - seg_start_out;
+          seg_start_out = C.out_pos; ++seg;
+          if (seg < B.nseg) seg_end += A.seg_len[B.seg_first + seg];
+        }
+        if (pos >= b1) break;
+        const u32 cur = in[pos];
+        const uint4 v = pb[PBIDX(n - 1, slot, pos - b0)];
+        enc5_bit(C, 0, 0);                                    // per-byte EOS flag, p = 0 (libzpaq.cpp:2426)
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit)
+          enc5_bit(C, (int)((cur >> (7 - bit)) & 1u), (u32)t_squash(S, vget(v, bit)) * 2u + 1u);
+      }
+      cs[0] = C.low; cs[1] = C.high; cs[2] = (u32)C.out_pos; cs[3] = (u32)(C.out_pos >> 32); cs[9] = (u32)C.status;
+      cs[4] = seg; cs[5] = (u32)seg_end; cs[6] = (u32)(seg_end >> 32); cs[7] = (u32)seg_start_out; cs[8] = (u32)(seg_start_out >> 32);
+      if (b1 >= N) { A.status[bi] = C.status; A.out_len[bi] = C.out_pos; }
+      return;
+    }
+    if (c >= n) return;
+    const ZComp cd = ZM->comp[c];
+    const u32 type = cd.type;
+    if (type == ZT_MIX) return;                                  // mixers have their own warps below
+    const int ch = W.wave - (int)ZM->pipe.depth[c];
+    if (ch < 0) return;
+    const int b0 = ch * CB;
+    if (b0 >= N) return;
+    const int b1 = min(N, b0 + CB);
+    const int slot = ch & 15;
+
+    const u32 a1 = cd.a1, a2 = cd.a2, a3 = cd.a3, a4 = cd.a4, a5 = cd.a5;
+    const u32 cm_mask = cd.cm_mask, ht_mask = cd.ht_mask, limit = cd.limit;
+    u32* const gtab = reinterpret_cast<u32*>(arena + (u64)cd.cm_off16 * 16);
+    u8* const ht = arena + (u64)cd.ht_off16 * 16;
+    const u32* const fops = ZM->wave.flat[c];
+    const u32 flen = ZM->wave.flat_len[c];
+    const u32 dist_byte = ZM->pipe.dist_byte[c];
+    const bool is_hash = (type == ZT_ICM || type == ZT_ISSE);
+
+    u32 h = cs[0];
+    u32 st[ZPQ_FLAT_SEGS] = {cs[1], cs[2], cs[3], cs[4]};
+    u64 hist = (u64)cs[5] | (u64)cs[6] << 32;
+    u32 dist_last = cs[7];
+    u32 ma = cs[8], mb = cs[9], mpos = cs[10], mpred = cs[11], mc = 0;
+    u32 h_next = h;
+    int p = (type == ZT_CONS) ? ((int)a1 - 128) * 4 : 0;
+    uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
+    uint4 pf0 = row, pf1 = row, pf2 = row; u32 pf_h0 = 0; bool pf_valid = false;
+    u32 bh = 0, v0 = 0, v1 = 0, cxt = 0; int xj = 0, xk = 0;
+
+    for (int pos = b0; pos < b1; ++pos) {
+      const u32 cur = in[pos];
+      const int i = pos - b0;
+      uint4 vin_j = make_uint4(0, 0, 0, 0), vin_k = vin_j;
+      if (type == ZT_ISSE || type == ZT_SSE) vin_j = pb[PBIDX(a2, slot, i)];
+      else if (type == ZT_MIX2) { vin_j = pb[PBIDX(a2, slot, i)]; vin_k = pb[PBIDX(a3, slot, i)]; }
+      else if (type == ZT_AVG) { vin_j = pb[PBIDX(a1, slot, i)]; vin_k = pb[PBIDX(a2, slot, i)]; }
+      uint4 vout = make_uint4(0, 0, 0, 0);
+
+#pragma unroll 1
+      for (int bit = 0; bit < 8; ++bit) {
+        const u32 c8 = (0x100u | cur) >> (8 - bit);
+        const u32 hmap4 = bit < 4 ? c8 : ((((0x10u | (cur >> 4)) << 4)) | ((0x10u | (cur & 15u)) >> (8 - bit)));
+        const int y = (int)((cur >> (7 - bit)) & 1u);
+        const int hslot = (int)(hmap4 & 15u);
+
+        if ((bit & 3) == 0) {
+          if (bit == 4) {
+            const u64 hs = (hist << 8) | (u64)cur;
+            if (cur == dist_byte) dist_last = (u32)(-(pos + 1));
+            h_next = flat_eval(fops, flen, st, cur, hs, pos, in, dist_last);
+            hist = hs;
+          }
+          if (is_hash) {
+            // Predictor::find (libzpaq.cpp:2072-2088) on rows requested one nibble ago
+            const u32 cx = h + 16u * c8;
+            const u32 chk = (cx >> (a1 + 2)) & 255u;
+            const u32 h0 = (cx * 16u) & ht_mask;
+            uint4 r0, r1, r2;
+            if (pf_valid && pf_h0 == h0) { r0 = pf0; r1 = pf1; r2 = pf2; }
+            else {
+              r0 = *reinterpret_cast<const uint4*>(ht + h0);
+              r1 = *reinterpret_cast<const uint4*>(ht + (h0 ^ 16u));
+              r2 = *reinterpret_cast<const uint4*>(ht + (h0 ^ 32u));
+            }
+            if ((r0.x & 255u) == chk) { row = r0; row_off = h0; }
+            else if ((r1.x & 255u) == chk) { row = r1; row_off = h0 ^ 16u; }
+            else if ((r2.x & 255u) == chk) { row = r2; row_off = h0 ^ 32u; }
+            else {
+              const u32 q0 = (r0.x >> 8) & 255u, q1 = (r1.x >> 8) & 255u, q2 = (r2.x >> 8) & 255u;
+              if (q0 <= q1 && q0 <= q2) row_off = h0;
+              else if (q1 < q2) row_off = h0 ^ 16u;
+              else row_off = h0 ^ 32u;
+              row = make_uint4(chk, 0, 0, 0);
+            }
+            const u32 ncx = bit == 0 ? (h + 16u * (0x10u | (cur >> 4))) : (h_next + 16u);
+            const u32 nh0 = (ncx * 16u) & ht_mask;
+            pf_valid = ((nh0 ^ row_off) & ~63u) != 0u && (bit == 0 || pos + 1 < b1);
+            if (pf_valid) {
+              pf_h0 = nh0;
+              pf0 = *reinterpret_cast<const uint4*>(ht + nh0);
+              pf1 = *reinterpret_cast<const uint4*>(ht + (nh0 ^ 16u));
+              pf2 = *reinterpret_cast<const uint4*>(ht + (nh0 ^ 32u));
+            }
+          }
+        }
+
+        // ---- predict (libzpaq.cpp:1854-1951) ----
+        switch (type) {
+          case ZT_ICM:
+            bh = row_get(row, hslot);
+            v0 = gtab[bh];
+            p = t_stretch(S, v0 >> 8);
+            break;
+          case ZT_ISSE: {
+            bh = row_get(row, hslot);
+            const uint2 w = *reinterpret_cast<const uint2*>(gtab + bh * 2);
+            v0 = w.x; v1 = w.y; xj = vget(vin_j, bit);
+            p = clamp2k(((int)v0 * xj + (int)v1 * 64) >> 16);
+            break;
+          }
+          case ZT_CM:
+            cxt = (h ^ hmap4) & cm_mask;
+            v0 = gtab[cxt];
+            p = t_stretch(S, v0 >> 17);
+            break;
+          case ZT_MATCH:
+            if (ma == 0) p = 0;
+            else {
+              mc = (mpred >> (7 - bit)) & 1u;
+              p = t_stretch(S, (u32)((int)S.dt2k[ma] * (1 - 2 * (int)mc)) & 32767u);
+            }
+            break;
+          case ZT_MIX2: {
+            cxt = (h + (c8 & a5)) & cm_mask;
+            const int w = (int)reinterpret_cast<const u16*>(gtab)[cxt];
+            v0 = (u32)w; xj = vget(vin_j, bit); xk = vget(vin_k, bit);
+            p = (w * xj + (65536 - w) * xk) >> 16;
+            break;
+          }
+          case ZT_AVG:
+            p = (vget(vin_j, bit) * (int)a3 + vget(vin_k, bit) * (256 - (int)a3)) >> 8;
+            break;
+          case ZT_SSE: {
+            const u32 rb = ((h + c8) * 32u) & cm_mask;
+            int pq = min(max(vget(vin_j, bit) + 992, 0), 1983);
+            const int wt = pq & 63;
+            pq >>= 6;
+            const u32 q0 = gtab[rb + (u32)pq], q1 = gtab[rb + (u32)pq + 1u];
+            p = t_stretch(S, (u32)(((int)(q0 >> 10) * (64 - wt) + (int)(q1 >> 10) * wt) >> 13));
+            if (wt >> 5) { cxt = rb + (u32)pq + 1u; v0 = q1; } else { cxt = rb + (u32)pq; v0 = q0; }
+            break;
+          }
+          default: break;   // CONS keeps its constant
+        }
+
+        // ---- update (libzpaq.cpp:1954-2052) ----
+        switch (type) {
+          case ZT_ICM: case ZT_ISSE: {
+            const u32 nx = ((u32)S.ns[bh] >> (8 * y)) & 255u;
+            row_set(row, hslot, nx);
+            if (type == ZT_ISSE) {
+              const int err = y * 32767 - t_squash(S, p);
+              const int w0 = clamp512k((int)v0 + ((err * xj + (1 << 12)) >> 13));
+              const int w1 = clamp512k((int)v1 + ((err + 16) >> 5));
+              *reinterpret_cast<uint2*>(gtab + bh * 2) = make_uint2((u32)w0, (u32)w1);
+            } else {
+              gtab[bh] = v0 + (u32)(((int)(y * 32767 - (int)(v0 >> 8))) >> 2);
+            }
+            if ((bit & 3) == 3) *reinterpret_cast<uint4*>(ht + row_off) = row;
+            break;
+          }
+          case ZT_CM: case ZT_SSE: {
+            const u32 count = v0 & 0x3ffu;
+            const int err = y * 32767 - (int)(v0 >> 17);
+            const u32 prod = (u32)err * ((u32)S.dt[count] * 2u);
+            gtab[cxt] = v0 + (prod & 0xfffffc00u) + (count < limit ? 1u : 0u);
+            break;
+          }
+          case ZT_MIX2: {
+            const int err = ((y * 32767 - t_squash(S, p)) * (int)a4) >> 5;
+            int w = (int)v0;
+            w += (err * (xj - xk) + (1 << 12)) >> 13;
+            w = min(max(w, 0), 65535);
+            reinterpret_cast<u16*>(gtab)[cxt] = (u16)w;
+            break;
+          }
+          case ZT_MATCH:
+            if ((int)mc != y) ma = 0;
+            if (bit == 7) {
+              ht[mpos] = (u8)cur;
+              mpos = (mpos + 1) & ht_mask;
+              u32* idx = gtab + (h & cm_mask);
+              if (ma == 0) {
+                mb = mpos - *idx;
+                if (mb & ht_mask)
+                  while (ma < 255 && ht[(mpos - ma - 1) & ht_mask] == ht[(mpos - ma - mb - 1) & ht_mask]) ++ma;
+              }
+              else ma += (ma < 255);
+              *idx = mpos;
+              mpred = ht[(mpos - mb) & ht_mask];
+            }
+            break;
+          default: break;
+        }
+        vset(vout, bit, p);
+      }
+      pb[PBIDX(c, slot, i)] = vout;
+      h = h_next;
+    }
+    cs[0] = h; cs[1] = st[0]; cs[2] = st[1]; cs[3] = st[2]; cs[4] = st[3];
+    cs[5] = (u32)hist; cs[6] = (u32)(hist >> 32); cs[7] = dist_last;
+    cs[8] = ma; cs[9] = mb; cs[10] = mpos; cs[11] = mpred;
+    return;
+  }
+
+  // =========================================================================================
+  // MIX warps: warp = (block, mixer); lane l = input l
+  // =========================================================================================
+  {
+    const int idx = gw - nA;
+    const int bi = idx / ZPQ_FAST_MIX, q = idx - bi * ZPQ_FAST_MIX;
+    if (bi >= A.nblk) return;
+    const ZBlock B = A.blocks[bi];
+    const ZModel* __restrict__ ZM = A.models + B.model;
+    if (q >= (int)ZM->team.nmix) return;
+    const int cq = (int)ZM->team.mix_comp[q];
+    const ZComp cd = ZM->comp[cq];
+    const int ch = W.wave - (int)ZM->pipe.depth[cq];
+    if (ch < 0) return;
+    int N = 0;
+    for (u32 sg = 0; sg < B.nseg; ++sg) N += (int)A.seg_len[B.seg_first + sg];
+    const int b0 = ch * CB;
+    if (b0 >= N) return;
+    const int b1 = min(N, b0 + CB);
+    const int slot = ch & 15;
+    const u8* const in = A.in + B.in_off;
+    u8* const arena = A.arena + B.arena_off;
+    int* const tab = reinterpret_cast<int*>(arena + (u64)cd.cm_off16 * 16);
+    const int g = (int)W.blk_group[bi], bl = (int)W.blk_lane[bi];
+    uint4* const pb = W.pbuf + (size_t)g * NCS * 16 * CB * 32;
+#define PBIDX2(comp, slot, i) ((((size_t)(comp) * 16 + (slot)) * CB + (i)) * 32 + bl)
+    u32* const cs = W.cstate + ((size_t)bi * NCS + cq) * CS_WORDS;
+    const int m = (int)cd.a3, j0 = (int)cd.a2, rate = (int)cd.a4;
+    const u32 a5 = cd.a5, cmm = cd.cm_mask;
+    const u32* const fops = ZM->wave.flat[cq];
+    const u32 flen = ZM->wave.flat_len[cq];
+
+    u32 h = cs[0];
+    u32 st[ZPQ_FLAT_SEGS] = {cs[1], cs[2], cs[3], cs[4]};
+    u64 hist = (u64)cs[5] | (u64)cs[6] << 32;
+    u32 h_next = h;
+    int w = 0; u32 wbase = 0; bool wvalid = false;
+
+    for (int pos = b0; pos < b1; ++pos) {
+      const u32 cur = in[pos];
+      const int i = pos - b0;
+      uint4 vin = make_uint4(0, 0, 0, 0);
+      if (lane < m) vin = pb[PBIDX2(j0 + lane, slot, i)];
+      uint4 vout = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+      for (int bit = 0; bit < 8; ++bit) {
+        if (bit == 4) {
+          const u64 hs = (hist << 8) | (u64)cur;
+          h_next = flat_eval(fops, flen, st, cur, hs, pos, in, 0u);
+          hist = hs;
+        }
+        const u32 c8 = (0x100u | cur) >> (8 - bit);
+        const int y = (int)((cur >> (7 - bit)) & 1u);
+        const u32 base = ((h + (c8 & a5)) & cmm) * (u32)m;
+        int wc;
+        if (wvalid && wbase == base) wc = w;                       // fetched (or trained) during the previous bit
+        else wc = lane < m ? tab[base + lane] : 0;
+        // request the next bit's weight row now: its index depends only on input data
+        u32 nbase; bool nvalid;
+        if (bit < 7) { const u32 nc8 = (0x100u | cur) >> (7 - bit); nbase = ((h + (nc8 & a5)) & cmm) * (u32)m; nvalid = true; }
+        else { nbase = ((h_next + (1u & a5)) & cmm) * (u32)m; nvalid = pos + 1 < b1; }
+        int wn = 0;
+        if (nvalid && nbase != base && lane < m) wn = tab[nbase + lane];
+        const int x = vget(vin, bit);
+        const int sum = __reduce_add_sync(FULL, lane < m ? (wc >> 8) * x : 0);
+        const int p = clamp2k(sum >> 8);
+        const int err = ((y * 32767 - t_squash(S, p)) * rate) >> 4;
+        const int wu = clamp512k(wc + ((err * x + (1 << 12)) >> 13));
+        if (lane < m) tab[base + lane] = wu;
+        w = (nbase == base) ? wu : wn; wbase = nbase; wvalid = nvalid;
+        vset(vout, bit, p);
+      }
+      if (lane == 0) pb[PBIDX2(cq, slot, i)] = vout;
+      h = h_next;
+    }
+    if (lane == 0) {
+      cs[0] = h; cs[1] = st[0]; cs[2] = st[1]; cs[3] = st[2]; cs[4] = st[3];
+      cs[5] = (u32)hist; cs[6] = (u32)(hist >> 32);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+extern "C" cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st) {
+  const int warps = w->ngroups * w->ncs + w->A.nblk * ZPQ_FAST_MIX;
+  if (warps <= 0) return cudaSuccess;
+  const int ctas = (warps + 3) / 4;
+  zpq_wave_kernel<<<ctas, 128, S2_STATIC, st>>>(*w);
+  return cudaGetLastError();
+}

@@ -472,6 +472,7 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
     }
     T.ok = ok ? 1 : 0;
   }
+  build_wave_plan(M);
   return ZPQ_OK;
 }
 
