@@ -323,7 +323,12 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           } else {
             const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, room / pw));
             if (cls == 2) CK(zpq_launch_enc3(&Ak, cnt, ctx->sm_count, warps, (int)pw, st), "zpq_enc_kernel3 launch");
-            else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, st), "zpq_code_kernel2 launch");
+            else {
+              unsigned long long sig = zpq_code2_signature(&models[jobs[wave[first]].model].fast);
+              for (int k = first + 1; k < first + cnt; ++k)
+                if (zpq_code2_signature(&models[jobs[wave[k]].model].fast) != sig) { sig = 0; break; }
+              CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, sig, st), "zpq_code_kernel2 launch");
+            }
           }
           ++ctx->launches;
         }

@@ -18,7 +18,8 @@ int zpq_code2_static_smem(void);
 cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st);
 cudaError_t zpq_launch_enc4(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, cudaStream_t st);
 cudaError_t zpq_launch_enc3(const ZKernelArgs* a, int nblk, int sm_count, int warps, int pw_bytes, cudaStream_t st);
+unsigned long long zpq_code2_signature(const ZFast* F);
 cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int decode, int sm_count, int warps, int pw_bytes,
-                             cudaStream_t st);
+                             unsigned long long sig, cudaStream_t st);
 }
 #endif

@@ -251,6 +251,9 @@ struct Plan {
 #define MIXX_SET(M, q, v) do { if ((q) == 0) (M).mixx0 = (v); else if ((q) == 1) (M).mixx1 = (v); else (M).mixx2 = (v); } while (0)
 
 // Predictor::predict0 (libzpaq.cpp:1854-1951)
+// SIG != 0: compile-time step signature (3 bits per step, 0 terminates): the step list of the two
+// makeConfig families is known, so their kernels contain exactly the code of their steps.
+template <unsigned long long SIG>
 __device__ __forceinline__ int predict2(Lane2& L, Plan& M, const Tabs& S, const u32* sm32, int lane) {
   const int c8 = M.c8, hmap4 = M.hmap4;
   const bool nib = (c8 == 1) || ((c8 & 0xf0) == 16);
@@ -303,9 +306,10 @@ __device__ __forceinline__ int predict2(Lane2& L, Plan& M, const Tabs& S, const 
   // ---- dependent components ----
 #pragma unroll
   for (int s = 0; s < ZPQ_FAST_STEPS; ++s) {
-    if (s < M.nsteps) {
+    const u32 ksig = (u32)((SIG >> (3 * s)) & 7ull);
+    if (SIG ? (ksig != 0u) : (s < M.nsteps)) {
       const u32 d = M.sd[s];
-      const u32 kind = d & 7u;
+      const u32 kind = SIG ? ksig : (d & 7u);
       const int owner = (int)((d >> 3) & 31u), sj = (int)((d >> 8) & 31u), sk = (int)((d >> 13) & 63u);
       if (kind == ZK_ISSE) {
         const int pj = __shfl_sync(FULL, L.p, (int)L.a2 & 31);
@@ -415,7 +419,7 @@ __device__ __forceinline__ void update2(Lane2& L, Plan& M, const Tabs& S, u32* s
 }
 
 // ---------------------------------------------------------------------------
-template <bool DEC>
+template <bool DEC, unsigned long long SIG>
 __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, const int pw_bytes) {
   extern __shared__ __align__(16) unsigned char smem[];
   {
@@ -550,7 +554,7 @@ __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, 
           if (eos) { if (C.curr != 0) status = ST_EOS; break; }
         }
         for (int bit = 7; bit >= 0; --bit) {
-          const u32 p16 = (u32)predict2(L, M, S, sm32, lane) * 2u + 1u;
+          const u32 p16 = (u32)predict2<SIG>(L, M, S, sm32, lane) * 2u + 1u;
           int y;
           if constexpr (!DEC) { y = (cbyte >> bit) & 1; enc_bit(C, lane, y, p16); }
           else {
@@ -600,21 +604,43 @@ __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, 
 // ---------------------------------------------------------------------------
 extern "C" int zpq_code2_static_smem(void) { return S2_STATIC; }
 
-extern "C" cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int decode, int sm_count, int warps, int pw_bytes,
-                                        cudaStream_t st) {
-  if (nblk <= 0) return cudaSuccess;
-  const size_t smem = (size_t)S2_STATIC + (size_t)warps * pw_bytes;
+// step signatures of the makeConfig families (ZK_ISSE=1 MIX=2 MIX2=3 SSE=4): 3 bits per step
+#define SIG3(a, b, c, d) ((unsigned long long)(a) | (unsigned long long)(b) << 3 | (unsigned long long)(c) << 6 | (unsigned long long)(d) << 9)
+static const unsigned long long kSigL4 = SIG3(1, 1, 1, 1) | SIG3(1, 2, 0, 0) << 12;                               // -method 4: 5 ISSE levels, MIX
+static const unsigned long long kSigL5 = SIG3(1, 1, 1, 1) | SIG3(1, 1, 1, 2) << 12 | SIG3(2, 3, 4, 3) << 24;      // -method 5: 7 ISSE levels, MIX, MIX, MIX2, SSE, MIX2
+
+template <bool DEC, unsigned long long SIG>
+static cudaError_t launch2(const ZKernelArgs* a, int ctas, int threads, size_t smem, int pw_bytes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(zpq_code_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(zpq_code_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(zpq_code_kernel2<DEC, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  zpq_code_kernel2<DEC, SIG><<<ctas, threads, smem, st>>>(*a, pw_bytes);
+  return cudaGetLastError();
+}
+
+extern "C" unsigned long long zpq_code2_signature(const ZFast* F) {
+  unsigned long long sig = 0;
+  for (uint32_t s = 0; s < F->nsteps && s < 16; ++s) sig |= (unsigned long long)(F->sd[s] & 7u) << (3 * s);
+  return sig;
+}
+
+// `sig`: common step signature of every block in the launch, or 0 (mixed / unknown: generic step loop)
+extern "C" cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int decode, int sm_count, int warps, int pw_bytes,
+                                        unsigned long long sig, cudaStream_t st) {
+  if (nblk <= 0) return cudaSuccess;
+  const size_t smem = (size_t)S2_STATIC + (size_t)warps * pw_bytes;
   int ctas = (nblk + warps - 1) / warps;
   if (ctas > sm_count) ctas = sm_count;            // persistent: one CTA per SM
-  if (decode) zpq_code_kernel2<true><<<ctas, warps * 32, smem, st>>>(*a, pw_bytes);
-  else zpq_code_kernel2<false><<<ctas, warps * 32, smem, st>>>(*a, pw_bytes);
-  return cudaGetLastError();
+  const int th = warps * 32;
+  if (decode) {
+    if (sig == kSigL5) return launch2<true, kSigL5>(a, ctas, th, smem, pw_bytes, st);
+    if (sig == kSigL4) return launch2<true, kSigL4>(a, ctas, th, smem, pw_bytes, st);
+    return launch2<true, 0ull>(a, ctas, th, smem, pw_bytes, st);
+  }
+  if (sig == kSigL5) return launch2<false, kSigL5>(a, ctas, th, smem, pw_bytes, st);
+  if (sig == kSigL4) return launch2<false, kSigL4>(a, ctas, th, smem, pw_bytes, st);
+  return launch2<false, 0ull>(a, ctas, th, smem, pw_bytes, st);
 }
