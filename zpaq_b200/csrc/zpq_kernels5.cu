@@ -202,6 +202,11 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
     uint4 pf0 = row, pf1 = row, pf2 = row; u32 pf_h0 = 0; bool pf_valid = false;
     u32 bh = 0, v0 = 0, v1 = 0, cxt = 0; int xj = 0, xk = 0;
+    // next-bit prefetch: the table entry the NEXT bit will use is known from input data, so it is
+    // requested while the current bit is computed; nx_* hold it, nx_key identifies it, and an entry that
+    // equals the one trained in this bit is replaced by the trained value (nx_same)
+    u32 nx_key = 0xffffffffu, nx_a = 0, nx_b = 0, up_a = 0, up_b = 0; bool nx_ok = false, nx_same = false;
+    u32 nx_key1 = 0xffffffffu;   // SSE: index of the second bucket (first is nx_key)
 
     for (int pos = b0; pos < b1; ++pos) {
       const u32 cur = in[pos];
@@ -218,6 +223,9 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
         const u32 hmap4 = bit < 4 ? c8 : ((((0x10u | (cur >> 4)) << 4)) | ((0x10u | (cur & 15u)) >> (8 - bit)));
         const int y = (int)((cur >> (7 - bit)) & 1u);
         const int hslot = (int)(hmap4 & 15u);
+        // context of the NEXT bit (bit 7: first bit of the next byte, c8 = hmap4 = 1)
+        const u32 c8n = bit < 7 ? ((0x100u | cur) >> (7 - bit)) : 1u;
+        const u32 hmap4n = bit < 3 ? c8n : (bit < 7 ? ((((0x10u | (cur >> 4)) << 4)) | ((0x10u | (cur & 15u)) >> (7 - bit))) : 1u);
 
         if ((bit & 3) == 0) {
           if (bit == 4) {
@@ -264,19 +272,36 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
         switch (type) {
           case ZT_ICM:
             bh = row_get(row, hslot);
-            v0 = gtab[bh];
+            if (nx_ok && nx_key == bh) v0 = nx_same ? up_a : nx_a;
+            else v0 = gtab[bh];
+            nx_ok = false;
+            if ((bit & 3) != 3) {                       // same row next bit: its slot is already final
+              nx_key = row_get(row, (int)(hmap4n & 15u)); nx_a = gtab[nx_key]; nx_ok = true;
+            }
             p = t_stretch(S, v0 >> 8);
             break;
           case ZT_ISSE: {
             bh = row_get(row, hslot);
-            const uint2 w = *reinterpret_cast<const uint2*>(gtab + bh * 2);
-            v0 = w.x; v1 = w.y; xj = vget(vin_j, bit);
+            if (nx_ok && nx_key == bh) { v0 = nx_same ? up_a : nx_a; v1 = nx_same ? up_b : nx_b; }
+            else { const uint2 w = *reinterpret_cast<const uint2*>(gtab + bh * 2); v0 = w.x; v1 = w.y; }
+            nx_ok = false;
+            if ((bit & 3) != 3) {
+              nx_key = row_get(row, (int)(hmap4n & 15u));
+              const uint2 wn = *reinterpret_cast<const uint2*>(gtab + nx_key * 2);
+              nx_a = wn.x; nx_b = wn.y; nx_ok = true;
+            }
+            xj = vget(vin_j, bit);
             p = clamp2k(((int)v0 * xj + (int)v1 * 64) >> 16);
             break;
           }
           case ZT_CM:
             cxt = (h ^ hmap4) & cm_mask;
-            v0 = gtab[cxt];
+            if (nx_ok && nx_key == cxt) v0 = nx_same ? up_a : nx_a;
+            else v0 = gtab[cxt];
+            nx_ok = false;
+            if (bit < 7 || pos + 1 < b1) {
+              nx_key = ((bit < 7 ? h : h_next) ^ hmap4n) & cm_mask; nx_a = gtab[nx_key]; nx_ok = true;
+            }
             p = t_stretch(S, v0 >> 17);
             break;
           case ZT_MATCH:
@@ -301,7 +326,16 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
             int pq = min(max(vget(vin_j, bit) + 992, 0), 1983);
             const int wt = pq & 63;
             pq >>= 6;
-            const u32 q0 = gtab[rb + (u32)pq], q1 = gtab[rb + (u32)pq + 1u];
+            u32 q0, q1;
+            if (nx_ok && nx_key == rb + (u32)pq) { q0 = nx_a; q1 = nx_b; }
+            else { q0 = gtab[rb + (u32)pq]; q1 = gtab[rb + (u32)pq + 1u]; }
+            nx_ok = false;
+            if (bit < 7) {                               // next bit of the same byte: input prediction already here
+              const u32 rbn = ((h + c8n) * 32u) & cm_mask;
+              const int pqn = min(max(vget(vin_j, bit + 1) + 992, 0), 1983) >> 6;
+              nx_key = rbn + (u32)pqn; nx_key1 = nx_key + 1u;
+              nx_a = gtab[nx_key]; nx_b = gtab[nx_key1]; nx_ok = true;
+            }
             p = t_stretch(S, (u32)(((int)(q0 >> 10) * (64 - wt) + (int)(q1 >> 10) * wt) >> 13));
             if (wt >> 5) { cxt = rb + (u32)pq + 1u; v0 = q1; } else { cxt = rb + (u32)pq; v0 = q0; }
             break;
@@ -319,9 +353,12 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
               const int w0 = clamp512k((int)v0 + ((err * xj + (1 << 12)) >> 13));
               const int w1 = clamp512k((int)v1 + ((err + 16) >> 5));
               *reinterpret_cast<uint2*>(gtab + bh * 2) = make_uint2((u32)w0, (u32)w1);
+              up_a = (u32)w0; up_b = (u32)w1;
             } else {
-              gtab[bh] = v0 + (u32)(((int)(y * 32767 - (int)(v0 >> 8))) >> 2);
+              up_a = v0 + (u32)(((int)(y * 32767 - (int)(v0 >> 8))) >> 2);
+              gtab[bh] = up_a;
             }
+            nx_same = nx_ok && nx_key == bh;
             if ((bit & 3) == 3) *reinterpret_cast<uint4*>(ht + row_off) = row;
             break;
           }
@@ -329,7 +366,13 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
             const u32 count = v0 & 0x3ffu;
             const int err = y * 32767 - (int)(v0 >> 17);
             const u32 prod = (u32)err * ((u32)S.dt[count] * 2u);
-            gtab[cxt] = v0 + (prod & 0xfffffc00u) + (count < limit ? 1u : 0u);
+            up_a = v0 + (prod & 0xfffffc00u) + (count < limit ? 1u : 0u);
+            gtab[cxt] = up_a;
+            if (type == ZT_CM) nx_same = nx_ok && nx_key == cxt;
+            else if (nx_ok) {                            // SSE: patch whichever prefetched bucket was just trained
+              if (nx_key == cxt) nx_a = up_a;
+              if (nx_key1 == cxt) nx_b = up_a;
+            }
             break;
           }
           case ZT_MIX2: {
@@ -405,7 +448,7 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     u32 st[ZPQ_FLAT_SEGS] = {cs[1], cs[2], cs[3], cs[4]};
     u64 hist = (u64)cs[5] | (u64)cs[6] << 32;
     u32 h_next = h;
-    int w = 0; u32 wbase = 0; bool wvalid = false;
+    int w_ld = 0, w_upd = 0; u32 wbase = 0; bool wvalid = false, wsame = false;
 
     for (int pos = b0; pos < b1; ++pos) {
       const u32 cur = in[pos];
@@ -424,7 +467,7 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
         const int y = (int)((cur >> (7 - bit)) & 1u);
         const u32 base = ((h + (c8 & a5)) & cmm) * (u32)m;
         int wc;
-        if (wvalid && wbase == base) wc = w;                       // fetched (or trained) during the previous bit
+        if (wvalid && wbase == base) wc = wsame ? w_upd : w_ld;   // fetched (or trained) during the previous bit
         else wc = lane < m ? tab[base + lane] : 0;
         // request the next bit's weight row now: its index depends only on input data
         u32 nbase; bool nvalid;
@@ -438,7 +481,7 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
         const int err = ((y * 32767 - t_squash(S, p)) * rate) >> 4;
         const int wu = clamp512k(wc + ((err * x + (1 << 12)) >> 13));
         if (lane < m) tab[base + lane] = wu;
-        w = (nbase == base) ? wu : wn; wbase = nbase; wvalid = nvalid;
+        w_ld = wn; w_upd = wu; wsame = (nbase == base); wbase = nbase; wvalid = nvalid;   // wn is first read next bit
         vset(vout, bit, p);
       }
       if (lane == 0) pb[PBIDX2(cq, slot, i)] = vout;
