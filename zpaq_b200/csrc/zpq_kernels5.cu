@@ -208,13 +208,23 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     u32 nx_key = 0xffffffffu, nx_a = 0, nx_b = 0, up_a = 0, up_b = 0; bool nx_ok = false, nx_same = false;
     u32 nx_key1 = 0xffffffffu;   // SSE: index of the second bucket (first is nx_key)
 
+    // inputs of byte pos+1 are requested while byte pos is coded
+    const u32 in_j = (type == ZT_AVG) ? a1 : a2, in_k = (type == ZT_AVG) ? a2 : a3;
+    const bool has_j = (type == ZT_ISSE || type == ZT_SSE || type == ZT_MIX2 || type == ZT_AVG);
+    const bool has_k = (type == ZT_MIX2 || type == ZT_AVG);
+    u32 cur_n = in[b0];
+    uint4 vj_n = make_uint4(0, 0, 0, 0), vk_n = vj_n;
+    if (has_j) vj_n = pb[PBIDX(in_j, slot, 0)];
+    if (has_k) vk_n = pb[PBIDX(in_k, slot, 0)];
     for (int pos = b0; pos < b1; ++pos) {
-      const u32 cur = in[pos];
+      const u32 cur = cur_n;
       const int i = pos - b0;
-      uint4 vin_j = make_uint4(0, 0, 0, 0), vin_k = vin_j;
-      if (type == ZT_ISSE || type == ZT_SSE) vin_j = pb[PBIDX(a2, slot, i)];
-      else if (type == ZT_MIX2) { vin_j = pb[PBIDX(a2, slot, i)]; vin_k = pb[PBIDX(a3, slot, i)]; }
-      else if (type == ZT_AVG) { vin_j = pb[PBIDX(a1, slot, i)]; vin_k = pb[PBIDX(a2, slot, i)]; }
+      const uint4 vin_j = vj_n, vin_k = vk_n;
+      if (pos + 1 < b1) {
+        cur_n = in[pos + 1];
+        if (has_j) vj_n = pb[PBIDX(in_j, slot, i + 1)];
+        if (has_k) vk_n = pb[PBIDX(in_k, slot, i + 1)];
+      }
       uint4 vout = make_uint4(0, 0, 0, 0);
 
 #pragma unroll 1
@@ -450,11 +460,17 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     u32 h_next = h;
     int w_ld = 0, w_upd = 0; u32 wbase = 0; bool wvalid = false, wsame = false;
 
+    u32 cur_n = in[b0];
+    uint4 vin_n = make_uint4(0, 0, 0, 0);
+    if (lane < m) vin_n = pb[PBIDX2(j0 + lane, slot, 0)];
     for (int pos = b0; pos < b1; ++pos) {
-      const u32 cur = in[pos];
+      const u32 cur = cur_n;
       const int i = pos - b0;
-      uint4 vin = make_uint4(0, 0, 0, 0);
-      if (lane < m) vin = pb[PBIDX2(j0 + lane, slot, i)];
+      const uint4 vin = vin_n;
+      if (pos + 1 < b1) {
+        cur_n = in[pos + 1];
+        if (lane < m) vin_n = pb[PBIDX2(j0 + lane, slot, i + 1)];
+      }
       uint4 vout = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
       for (int bit = 0; bit < 8; ++bit) {
