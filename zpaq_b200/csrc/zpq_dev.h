@@ -128,7 +128,7 @@ struct ZWave {
   uint32_t ok;
   uint32_t dcoder;                         // depth of the coder stage = depth[n-1] + 1
   uint32_t flat_len[ZPQ_MAX_LANES];
-  uint32_t flat[ZPQ_MAX_LANES][ZPQ_FLAT_MAX];
+  alignas(16) uint32_t flat[ZPQ_MAX_LANES][ZPQ_FLAT_MAX];   // rows of 160 bytes, fetched 16 bytes at a time
 };
 
 // Team plan (zpq_kernels4.cu): the skewed pipeline of ZPipe split over THREE warps per block so that
