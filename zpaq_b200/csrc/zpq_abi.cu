@@ -327,7 +327,15 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
               unsigned long long sig = zpq_code2_signature(&models[jobs[wave[first]].model].fast);
               for (int k = first + 1; k < first + cnt; ++k)
                 if (zpq_code2_signature(&models[jobs[wave[k]].model].fast) != sig) { sig = 0; break; }
-              CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, sig, st), "zpq_code_kernel2 launch");
+              bool pair = decode && kv >= 5;
+              for (int k = first; k < first + cnt && pair; ++k) pair = models[jobs[wave[k]].model].fast.pair_ok != 0;
+              if (pair) {
+                // two warps per block (zpq_kernels6.cu)
+                const uint64_t room6 = ZPQ_SMEM_MAX - (uint64_t)zpq_dec6_static_smem();
+                const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room6 / (pw + (uint64_t)zpq_dec6_ctrl_bytes())));
+                CK(zpq_launch_dec6(&Ak, cnt, ctx->sm_count, teams, (int)pw, sig, st), "zpq_dec_kernel6 launch");
+              }
+              else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, sig, st), "zpq_code_kernel2 launch");
             }
           }
           ++ctx->launches;

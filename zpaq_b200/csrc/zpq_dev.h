@@ -67,6 +67,8 @@ struct ZFast {
   uint32_t pw_bytes;                  // shared memory per block: all ICM (1 KB) and ISSE (2 KB) tables
   uint32_t smem_off[ZPQ_MAX_LANES];   // byte offset of the lane's table inside the block's shared region
   uint8_t level[ZPQ_MAX_LANES];       // ISSE lanes: dependency level (1 = fed by a phase-A component)
+  uint32_t pair_ok;                   // two-warp decoder (zpq_kernels6.cu) usable: set after the wave plan
+  uint32_t nlev;                      // number of ISSE levels
 };
 
 

@@ -76,6 +76,82 @@ __device__ __forceinline__ void d_find(u8* ht, u32 ht_mask, int shift, u32 cxt, 
 }
 
 
+// ---- eight int16 predictions in one 16-byte vector; flattened context recipes (zpq_hcomp.cpp) ----
+__device__ __forceinline__ int vget(const uint4& v, int bit) {
+  const u32 w = (bit & 4) ? ((bit & 2) ? v.w : v.z) : ((bit & 2) ? v.y : v.x);
+  return (int)(short)(w >> ((bit & 1) * 16));
+}
+__device__ __forceinline__ void vset(uint4& v, int bit, int p) {
+  const u32 sh = (bit & 1) * 16;
+  const u32 keep = ~(0xffffu << sh), val = ((u32)p & 0xffffu) << sh;
+  if (bit & 4) { if (bit & 2) v.w = (v.w & keep) | val; else v.z = (v.z & keep) | val; }
+  else         { if (bit & 2) v.y = (v.y & keep) | val; else v.x = (v.x & keep) | val; }
+}
+
+// Flattened recipe (zpq_hcomp.cpp: build_wave_plan / FlatEval).  st[] = private segment states.
+// The op words are fetched four at a time (16-byte loads from the read-only path) so that the
+// interpreter loop does not pay one L1 round trip per op.
+struct FlatState { u32 acc, prev_new, prev_old; int k; bool skip; u32 w_pending; };
+
+// Byte sources older than 8 bytes: `in` is either the input stream (encode: in[bpos-off]) or, when
+// ring_mask != 0, the HCOMP M ring (decode: m[(C+off) & mask], exactly what the bytecode reads).
+__device__ __forceinline__ void flat_op(FlatState& F, u32 w, u32 wnext, u32 st[ZPQ_FLAT_SEGS], u32 cur, u64 hs, int bpos,
+                                        const u8* in, u32 dist_last, u32 vc, u32 ring_mask = 0) {
+  if (F.skip) { F.skip = false; return; }          // second word of a ZR_WORD op
+  const u32 op = w & 15u, src = (w >> 4) & 15u, arg = (w >> 8) & 255u, off = w >> 16;
+  if (op == ZR_END) return;
+  if (op == ZR_SEG) {
+    if (F.k >= 0) {
+      const u32 old = F.k == 0 ? st[0] : (F.k == 1 ? st[1] : (F.k == 2 ? st[2] : st[3]));
+      if (F.k == 0) st[0] = F.acc; else if (F.k == 1) st[1] = F.acc; else if (F.k == 2) st[2] = F.acc; else st[3] = F.acc;
+      F.prev_old = old; F.prev_new = F.acc;
+    }
+    ++F.k;
+    const u32 own = F.k == 0 ? st[0] : (F.k == 1 ? st[1] : (F.k == 2 ? st[2] : st[3]));
+    F.acc = src == ZB_ZERO ? 0u : (src == ZB_OWN ? own : F.prev_new);
+    return;
+  }
+  u32 x = 0;
+  if (src == ZS_BYTE) {
+    if (off < 8) x = (u32)(hs >> (off * 8)) & arg;
+    else if (ring_mask) x = (u32)in[(vc + off) & ring_mask] & arg;
+    else x = ((int)off <= bpos) ? ((u32)in[bpos - (int)off] & arg) : 0u;
+  }
+  else if (src == ZS_POSAND) x = vc & arg;
+  else if (src == ZS_POSMOD) x = arg ? vc % arg : 0u;
+  else if (src == ZS_DIST) x = min(dist_last - vc, 255u);
+  if (op == ZR_FOLD) F.acc = (F.acc + x + 512u) * 773u;
+  else if (op == ZR_SHL8ADD) F.acc = (F.acc << 8) + x;
+  else if (op == ZR_SHR) F.acc >>= arg;
+  else if (op == ZR_SHL) F.acc <<= arg;
+  else if (op == ZR_ROLL) F.acc = F.acc * off + cur + 1u;
+  else if (op == ZR_WORD) {
+    const u32 v2 = off & 255u, v3 = off >> 8, mult = wnext & 255u, first = (wnext >> 8) & 1u;
+    if ((((cur & arg) - v2) & 255u) < v3) F.acc = F.acc * mult + cur + 1u;
+    else F.acc = first ? 0u : F.prev_old;
+    F.skip = true;
+  }
+}
+
+__device__ __forceinline__ u32 flat_eval(const u32* __restrict__ ops, u32 len, u32 st[ZPQ_FLAT_SEGS], u32 cur, u64 hs,
+                                         int bpos, const u8* in, u32 dist_last, u32 ring_mask = 0) {
+  const u32 vc = (u32)(-(bpos + 1));
+  FlatState F; F.acc = 0; F.prev_new = 0; F.prev_old = 0; F.k = -1; F.skip = false; F.w_pending = 0;
+  const uint4* __restrict__ o4 = reinterpret_cast<const uint4*>(ops);     // rows are 160 bytes: 16-byte aligned
+  uint4 q = __ldg(o4);
+  for (u32 t = 0; t < len; t += 4) {
+    const uint4 qn = (t + 4 < len) ? __ldg(o4 + (t >> 2) + 1) : make_uint4(0, 0, 0, 0);
+    flat_op(F, q.x, q.y, st, cur, hs, bpos, in, dist_last, vc, ring_mask);
+    flat_op(F, q.y, q.z, st, cur, hs, bpos, in, dist_last, vc, ring_mask);
+    flat_op(F, q.z, q.w, st, cur, hs, bpos, in, dist_last, vc, ring_mask);
+    flat_op(F, q.w, qn.x, st, cur, hs, bpos, in, dist_last, vc, ring_mask);
+    q = qn;
+  }
+  if (F.k == 0) st[0] = F.acc; else if (F.k == 1) st[1] = F.acc; else if (F.k == 2) st[2] = F.acc; else if (F.k == 3) st[3] = F.acc;
+  return F.acc;
+}
+
+
 // Stage the CTA-wide tables into shared memory (call with all threads, then __syncthreads()).
 __device__ __forceinline__ void stage_tables(unsigned char* smem, const ZTables* T) {
   const uint4* src = reinterpret_cast<const uint4*>(T->stretch_hi);

@@ -15,6 +15,9 @@ cudaError_t zpq_launch_code(const ZKernelArgs* a, int nblk, int decode, int sm_c
 // v2 (production) kernel: one CTA per SM, `warps` blocks in flight per CTA,
 // `pw_bytes` of shared memory per warp for the ICM/ISSE tables.
 int zpq_code2_static_smem(void);
+int zpq_dec6_static_smem(void);
+int zpq_dec6_ctrl_bytes(void);
+cudaError_t zpq_launch_dec6(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, unsigned long long sig, cudaStream_t st);
 cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st);
 cudaError_t zpq_launch_enc4(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, cudaStream_t st);
 cudaError_t zpq_launch_enc3(const ZKernelArgs* a, int nblk, int sm_count, int warps, int pw_bytes, cudaStream_t st);

@@ -473,6 +473,17 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
     T.ok = ok ? 1 : 0;
   }
   build_wave_plan(M);
+  // two-warp decoder: needs the self-contained (flattened) recipes, and every ISSE fed by an ICM or ISSE
+  {
+    bool ok = M->fast.ok && M->wave.ok;
+    uint32_t nlev = 0;
+    for (uint32_t s = 0; s < M->fast.nsteps; ++s) if ((M->fast.sd[s] & 7u) == ZK_ISSE) ++nlev;
+    for (int i = 0; i < n && ok; ++i)
+      if (M->comp[i].type == ZT_ISSE) { const int t = M->comp[M->comp[i].a2].type; if (t != ZT_ICM && t != ZT_ISSE) ok = false; }
+    // ISSE levels must be the leading steps (they run in the first warp before anything else is known)
+    for (uint32_t s = 0; s < M->fast.nsteps && ok; ++s) if (((M->fast.sd[s] & 7u) == ZK_ISSE) != (s < nlev)) ok = false;
+    M->fast.pair_ok = ok ? 1 : 0; M->fast.nlev = nlev;
+  }
   return ZPQ_OK;
 }
 
