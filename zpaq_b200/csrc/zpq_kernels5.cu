@@ -183,6 +183,16 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
         const u32 hmap4n = bit < 3 ? c8n : (bit < 7 ? ((((0x10u | (cur >> 4)) << 4)) | ((0x10u | (cur & 15u)) >> (7 - bit))) : 1u);
 
         if ((bit & 3) == 0) {
+          // tables indexed per bit: pull the lines of the NEXT nibble into L2 now (addresses are input data)
+          if (type == ZT_CM) {
+            if (bit == 0) prefetch_l2(gtab + ((h ^ ((0x10u | (cur >> 4)) << 4)) & cm_mask));
+          }
+          else if (type == ZT_SSE) {
+#pragma unroll
+            for (int k = 2; k <= 5; ++k) {
+              if (bit + k < 8) prefetch_l2(gtab + (((h + ((0x100u | cur) >> (8 - bit - k))) * 32u) & cm_mask));
+            }
+          }
           if (bit == 4) {
             const u64 hs = (hist << 8) | (u64)cur;
             if (cur == dist_byte) dist_last = (u32)(-(pos + 1));
@@ -427,6 +437,11 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
         const u32 c8 = (0x100u | cur) >> (8 - bit);
         const int y = (int)((cur >> (7 - bit)) & 1u);
         const u32 base = ((h + (c8 & a5)) & cmm) * (u32)m;
+        if (bit < 5 && lane < 2) {                      // row of bit+3 (same byte) into L2: covers HBM + TLB latency
+          const u32 c83 = (0x100u | cur) >> (5 - bit);
+          const u32 b3 = ((h + (c83 & a5)) & cmm) * (u32)m;
+          prefetch_l2(tab + b3 + (lane ? (u32)m - 1u : 0u));
+        }
         int wc;
         if (wvalid && wbase == base) wc = wsame ? w_upd : w_ld;   // fetched (or trained) during the previous bit
         else wc = lane < m ? tab[base + lane] : 0;
