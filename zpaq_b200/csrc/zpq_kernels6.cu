@@ -152,12 +152,6 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           // ---- predict ----
           const bool nib = (c8 == 1) || ((c8 & 0xf0) == 16);
           if (mine) {
-            if (c8 >= 8 && c8 < 16) {
-              // one bit before the nibble boundary: the next nibble's row group has two candidates; pull both
-              // into L2 now so that find() does not wait for HBM (the three rows share one 64-byte group)
-              prefetch_l2(ht + ((((h + 16u * (u32)(c8 * 2)) * 16u) & ht_mask) & ~63u));
-              prefetch_l2(ht + ((((h + 16u * (u32)(c8 * 2 + 1)) * 16u) & ht_mask) & ~63u));
-            }
             if (nib) d_find(ht, ht_mask, (int)a1 + 2, h + 16u * (u32)c8, row, row_off);
             bh = row_get(row, hmap4 & 15);
             if (type == ZT_ISSE) {
@@ -262,28 +256,6 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           int cbyte = 0;
           bool failed = false;
           for (int bit = 7; bit >= 0; --bit) {
-            // ---- next bit: its context is 2*c8+y, so every bit-indexed table row has two candidates;
-            //      pull both into L2 one bit ahead (not across the byte boundary: h changes there) ----
-            if (c8 < 128) {
-              const u32 c80 = (u32)c8 * 2u, c81 = c80 + 1u;
-              if (type == ZT_CM) {
-                int hm0, hm1;
-                if (c80 >= 16 && c80 < 32) { hm0 = (hmap4 & 0xf) << 5 | 1; hm1 = hm0 | 16; }
-                else { hm0 = (hmap4 & 0x1f0) | (((hmap4 & 0xf) * 2) & 0xf); hm1 = (hmap4 & 0x1f0) | (((hmap4 & 0xf) * 2 + 1) & 0xf); }
-                prefetch_l2(gtab + ((h ^ (u32)hm0) & cm_mask));
-                prefetch_l2(gtab + ((h ^ (u32)hm1) & cm_mask));
-              }
-              else if (type == ZT_MIX) {
-                const int* t = reinterpret_cast<const int*>(gtab);
-                const u32 b0 = ((h + (c80 & a5)) & cm_mask) * a3, b1 = ((h + (c81 & a5)) & cm_mask) * a3;
-                prefetch_l2(t + b0); prefetch_l2(t + b0 + a3 - 1u);
-                prefetch_l2(t + b1); prefetch_l2(t + b1 + a3 - 1u);
-              }
-              else if (type == ZT_SSE) {
-                prefetch_l2(gtab + (((h + c80) * 32u) & cm_mask));
-                prefetch_l2(gtab + (((h + c81) * 32u) & cm_mask));
-              }
-            }
             // ---- own table lookups and early row fetches (overlap warp A's ISSE chain) ----
             if (type == ZT_CM) {
               cxt = (h ^ (u32)hmap4) & cm_mask;
