@@ -64,6 +64,7 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   uint64_t launches = 0;
+  int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
 };
 
@@ -283,7 +284,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
             dmaxc = std::max(dmaxc, models[J.model].wave.dcoder);
           }
           const int ngroups = (int)gfirst.size();
-          int CB = 2048;
+          int CB = ctx->wave_chunk;
           size_t fr = 0, tot = 0;
           CK(cudaMemGetInfo(&fr, &tot), "cudaMemGetInfo");
           while (CB > 128 && (uint64_t)ngroups * ncs * 16 * CB * 512 > (uint64_t)fr + ctx->d_pbuf.cap - ((uint64_t)1 << 30)) CB >>= 1;
@@ -452,6 +453,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return ZPQ_E_CUDA; }
   zpq_ctx* ctx = new zpq_ctx();
   ctx->device = device;
+  if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
   cudaDeviceProp prop;
