@@ -64,6 +64,7 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   uint64_t launches = 0;
+  int wave_group = 8;          // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
 };
@@ -273,11 +274,12 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
         if (cls == 4) { CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch"); ++ctx->launches; }
         else if (cls == 0) {
           // ---- wavefront encoder: groups of <= 32 blocks of one model, one launch per wave ----
+          const int GS = ctx->wave_group;
           std::vector<uint32_t> gfirst, gcount, bgroup(cnt), blane(cnt);
           int ncs = 2; uint64_t maxN = 0; uint32_t dmaxc = 0;
           for (int k = 0; k < cnt; ++k) {
             const IJob& J = jobs[wave[first + k]];
-            if (k == 0 || J.model != jobs[wave[first + k - 1]].model || gcount.back() == 32) { gfirst.push_back((uint32_t)k); gcount.push_back(0); }
+            if (k == 0 || J.model != jobs[wave[first + k - 1]].model || (int)gcount.back() == GS) { gfirst.push_back((uint32_t)k); gcount.push_back(0); }
             bgroup[k] = (uint32_t)gfirst.size() - 1; blane[k] = gcount.back()++;
             ncs = std::max(ncs, (int)models[J.model].n + 1);
             maxN = std::max(maxN, J.in_total);
@@ -287,8 +289,8 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           int CB = ctx->wave_chunk;
           size_t fr = 0, tot = 0;
           CK(cudaMemGetInfo(&fr, &tot), "cudaMemGetInfo");
-          while (CB > 128 && (uint64_t)ngroups * ncs * 16 * CB * 512 > (uint64_t)fr + ctx->d_pbuf.cap - ((uint64_t)1 << 30)) CB >>= 1;
-          const uint64_t pbytes = (uint64_t)ngroups * ncs * 16 * CB * 512, cbytes = (uint64_t)cnt * ncs * 64;
+          while (CB > 128 && (uint64_t)ngroups * ncs * 16 * CB * 16 * GS > (uint64_t)fr + ctx->d_pbuf.cap - ((uint64_t)1 << 30)) CB >>= 1;
+          const uint64_t pbytes = (uint64_t)ngroups * ncs * 16 * CB * 16 * GS, cbytes = (uint64_t)cnt * ncs * 64;
           CK(ctx->d_pbuf.reserve(pbytes), "prediction stream cudaMalloc");
           CK(ctx->d_cstate.reserve(cbytes + (uint64_t)(ngroups * 2 + cnt * 2) * 4 + 1024), "wave state cudaMalloc");
           uint8_t* dc = (uint8_t*)ctx->d_cstate.p;
@@ -305,7 +307,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           ZWaveArgs Wv;
           Wv.A = Ak; Wv.pbuf = (uint4*)ctx->d_pbuf.p; Wv.cstate = (uint32_t*)dc;
           Wv.group_first = d_gfirst; Wv.group_count = d_gcount; Wv.blk_group = d_bgroup; Wv.blk_lane = d_blane;
-          Wv.chunk_bytes = CB; Wv.ncs = ncs; Wv.ngroups = ngroups;
+          Wv.chunk_bytes = CB; Wv.ncs = ncs; Wv.ngroups = ngroups; Wv.gsize = GS;
           const int nwaves = (int)((maxN + CB - 1) / CB) + (int)dmaxc + 1;
           for (int w = 0; w < std::max(nwaves, (int)dmaxc + 1); ++w) {
             Wv.wave = w;
@@ -453,6 +455,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return ZPQ_E_CUDA; }
   zpq_ctx* ctx = new zpq_ctx();
   ctx->device = device;
+  if (const char* gs = getenv("ZPQ_GROUP")) { const int v = atoi(gs); if (v >= 1 && v <= 32) ctx->wave_group = v; }
   if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }

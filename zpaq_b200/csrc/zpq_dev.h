@@ -218,13 +218,14 @@ struct ZKernelArgs {
 // Arguments of the wavefront encode kernel (zpq_kernels5.cu), one launch per wave.
 struct ZWaveArgs {
   ZKernelArgs A;                 // blocks of this launch class, grouped: 32 consecutive blocks of one model = a group
-  uint4* pbuf;                   // prediction streams [group][component slot][16 chunk slots][chunk byte][lane]
+  uint4* pbuf;                   // prediction streams [group][component slot][16 chunk slots][chunk byte][lane < gsize]
   uint32_t* cstate;              // [block][component slot][16 words] state carried between waves (zeroed per batch)
   const uint32_t* group_first;   // first block index of each group
   const uint32_t* group_count;   // blocks in the group (<= 32)
   const uint32_t* blk_group;     // block -> group
   const uint32_t* blk_lane;      // block -> lane inside its group
   int wave, chunk_bytes, ncs, ngroups;   // ncs = component slots per block = max components + 1 (coder)
+  int gsize;                             // blocks per group (= active lanes of a component warp), <= 32
 };
 
 #endif

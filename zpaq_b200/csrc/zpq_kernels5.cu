@@ -8,9 +8,10 @@
 //     depth d codes chunk w-d, the coder (depth of the last component + 1) codes chunk w-dc;
 //   * a thread owns ONE component of ONE block for one chunk: its tables are private, its state (context
 //     hashes, MATCH pointers, coder range) is kept in a 64-byte record between waves;
-//   * the 32 lanes of a warp are the same component of 32 different blocks with the same model, so the
-//     per-type code path is warp-uniform (no SIMT divergence), and the SM hides HBM/L2 latency by
-//     switching among ~18 resident warps instead of stalling one;
+//   * the lanes of a warp are the same component of `gsize` different blocks with the same model, so the
+//     per-type code path is warp-uniform (no SIMT divergence); the loop is latency bound per warp, so
+//     the group size trades lanes for warps: 8 blocks per warp puts ~3 000 component warps on the GPU
+//     and lets every SM switch among 16 resident warps instead of 5;
 //   * predictions travel through HBM streams (one 16-byte vector of eight int16 per component per
 //     byte, laid out [group][component][chunk slot][byte][lane] so that a warp reads and writes 512
 //     contiguous bytes); a stream written in wave w is read in waves w+1 .. w+15;
@@ -75,8 +76,9 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     for (u32 sg = 0; sg < B.nseg; ++sg) N += (int)A.seg_len[B.seg_first + sg];
     const u8* const in = A.in + B.in_off;
     u32* const cs = W.cstate + ((size_t)bi * NCS + c) * CS_WORDS;
-    uint4* const pb = W.pbuf + (size_t)g * NCS * 16 * CB * 32;        // this group's streams
-#define PBIDX(comp, slot, i) ((((size_t)(comp) * 16 + (slot)) * CB + (i)) * 32 + lane)
+    const int GS = W.gsize;
+    uint4* const pb = W.pbuf + (size_t)g * NCS * 16 * CB * GS;        // this group's streams
+#define PBIDX(comp, slot, i) ((((size_t)(comp) * 16 + (slot)) * CB + (i)) * GS + lane)
 
     if (c == NCS - 1) {
       // ---------------- coder stage ----------------
@@ -401,8 +403,9 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     u8* const arena = A.arena + B.arena_off;
     int* const tab = reinterpret_cast<int*>(arena + (u64)cd.cm_off16 * 16);
     const int g = (int)W.blk_group[bi], bl = (int)W.blk_lane[bi];
-    uint4* const pb = W.pbuf + (size_t)g * NCS * 16 * CB * 32;
-#define PBIDX2(comp, slot, i) ((((size_t)(comp) * 16 + (slot)) * CB + (i)) * 32 + bl)
+    const int GS = W.gsize;
+    uint4* const pb = W.pbuf + (size_t)g * NCS * 16 * CB * GS;
+#define PBIDX2(comp, slot, i) ((((size_t)(comp) * 16 + (slot)) * CB + (i)) * GS + bl)
     u32* const cs = W.cstate + ((size_t)bi * NCS + cq) * CS_WORDS;
     const int m = (int)cd.a3, j0 = (int)cd.a2, rate = (int)cd.a4;
     const u32 a5 = cd.a5, cmm = cd.cm_mask;
