@@ -64,7 +64,7 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   uint64_t launches = 0;
-  int wave_group = 8;          // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
+  int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
 };
