@@ -48,7 +48,7 @@ __device__ __forceinline__ void enc5_bit(Enc5& C, int y, u32 p16) {
 
 #define CS_WORDS 16     // per (block, component) state record, in u32
 
-__global__ void __launch_bounds__(128, 5) zpq_wave_kernel(const ZWaveArgs W) {
+__global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
   extern __shared__ __align__(16) unsigned char smem[];
   stage_tables(smem, W.A.tables);
   __syncthreads();
