@@ -341,7 +341,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "alg_bytes_per_input_byte": balg, "kernel": "zpq_enc_kernel3 + zpq_code_kernel2<decode>",
+                         "alg_bytes_per_input_byte": balg, "kernel": "zpq_wave_kernel (encode, 525 launches per step) + zpq_dec_kernel6 (decode)",
                          "note": "latency/issue bound, not bandwidth bound (see profiles/ and DESIGN.md section 6)"},
             "cpu_baseline": cpu, "bit_exact_vs_reference": bit_exact, "clocks": clocks,
             "archive_ratio": r["arc_bytes"] / nbytes, "setup_s": gen_s,
