@@ -66,6 +66,9 @@ struct zpq_ctx {
   uint64_t launches = 0;
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
+  int wave_variant = 1;        // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches
+  int dec_variant = 3;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B
+  bool wave_prof = false;      // ZPQ_WAVE_PROF=1: per-role warp cycles of the wavefront encoder to stderr
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
 };
 
@@ -292,12 +295,13 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           while (CB > 128 && (uint64_t)ngroups * ncs * 16 * CB * 16 * GS > (uint64_t)fr + ctx->d_pbuf.cap - ((uint64_t)1 << 30)) CB >>= 1;
           const uint64_t pbytes = (uint64_t)ngroups * ncs * 16 * CB * 16 * GS, cbytes = (uint64_t)cnt * ncs * 64;
           CK(ctx->d_pbuf.reserve(pbytes), "prediction stream cudaMalloc");
-          CK(ctx->d_cstate.reserve(cbytes + (uint64_t)(ngroups * 2 + cnt * 2) * 4 + 1024), "wave state cudaMalloc");
+          CK(ctx->d_cstate.reserve(cbytes + (uint64_t)(ngroups * 2 + cnt * 2) * 4 + 2048), "wave state cudaMalloc");
           uint8_t* dc = (uint8_t*)ctx->d_cstate.p;
           uint32_t* d_gfirst = (uint32_t*)(dc + align_up(cbytes, 256));
           uint32_t* d_gcount = d_gfirst + ngroups;
           uint32_t* d_bgroup = d_gcount + ngroups;
           uint32_t* d_blane = d_bgroup + cnt;
+          unsigned long long* d_prof = (unsigned long long*)(((uintptr_t)(d_blane + cnt) + 15) & ~(uintptr_t)15);
           CK(cudaMemsetAsync(dc, 0, cbytes, st), "memset wave state");
           CK(cudaMemcpyAsync(d_gfirst, gfirst.data(), (size_t)ngroups * 4, cudaMemcpyHostToDevice, st), "H2D groups");
           CK(cudaMemcpyAsync(d_gcount, gcount.data(), (size_t)ngroups * 4, cudaMemcpyHostToDevice, st), "H2D groups");
@@ -308,11 +312,22 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           Wv.A = Ak; Wv.pbuf = (uint4*)ctx->d_pbuf.p; Wv.cstate = (uint32_t*)dc;
           Wv.group_first = d_gfirst; Wv.group_count = d_gcount; Wv.blk_group = d_bgroup; Wv.blk_lane = d_blane;
           Wv.chunk_bytes = CB; Wv.ncs = ncs; Wv.ngroups = ngroups; Wv.gsize = GS;
+          Wv.prof = nullptr;
+          if (ctx->wave_prof) { CK(cudaMemsetAsync(d_prof, 0, 64 * 8, st), "memset prof"); Wv.prof = d_prof; }
           const int nwaves = (int)((maxN + CB - 1) / CB) + (int)dmaxc + 1;
           for (int w = 0; w < std::max(nwaves, (int)dmaxc + 1); ++w) {
             Wv.wave = w;
-            CK(zpq_launch_wave(&Wv, st), "zpq_wave_kernel launch");
-            ++ctx->launches;
+            CK(zpq_launch_wave(&Wv, st, ctx->wave_variant), "zpq_wave_kernel launch");
+            ctx->launches += (ctx->wave_variant & 2) ? 2 : 1;
+          }
+          if (ctx->wave_prof) {
+            unsigned long long hp[64];
+            CK(cudaMemcpyAsync(hp, d_prof, sizeof hp, cudaMemcpyDeviceToHost, st), "D2H prof");
+            CK(cudaStreamSynchronize(st), "sync");
+            static const char* const rn[14] = {"none", "const", "cm", "icm", "match", "avg", "mix2", "mix(thread)", "isse", "sse", "coder", "mix warp 0", "mix warp 1", "mix warp 2"};
+            for (int r = 0; r < 14; ++r)
+              if (hp[2 * r + 1]) fprintf(stderr, "[zpq wave prof] %-12s warps %9llu  cycles/warp %10.0f  cycles/bit %8.1f\n", rn[r], hp[2 * r + 1],
+                                         (double)hp[2 * r] / (double)hp[2 * r + 1], (double)hp[2 * r] / (double)hp[2 * r + 1] / (8.0 * CB));
           }
         }
         else {
@@ -336,7 +351,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
                 // two warps per block (zpq_kernels6.cu)
                 const uint64_t room6 = ZPQ_SMEM_MAX - (uint64_t)zpq_dec6_static_smem();
                 const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room6 / (pw + (uint64_t)zpq_dec6_ctrl_bytes())));
-                CK(zpq_launch_dec6(&Ak, cnt, ctx->sm_count, teams, (int)pw, sig, st), "zpq_dec_kernel6 launch");
+                CK(zpq_launch_dec6(&Ak, cnt, ctx->sm_count, teams, (int)pw, sig, ctx->dec_variant, st), "zpq_dec_kernel6 launch");
               }
               else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, sig, st), "zpq_code_kernel2 launch");
             }
@@ -457,6 +472,9 @@ int zpq_create(int device, zpq_ctx** out) {
   ctx->device = device;
   if (const char* gs = getenv("ZPQ_GROUP")) { const int v = atoi(gs); if (v >= 1 && v <= 32) ctx->wave_group = v; }
   if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
+  if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 3) ctx->wave_variant = v; }
+  if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if (v >= 0 && v <= 3) ctx->dec_variant = v; }
+  if (const char* wp = getenv("ZPQ_WAVE_PROF")) ctx->wave_prof = atoi(wp) != 0;
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
   cudaDeviceProp prop;

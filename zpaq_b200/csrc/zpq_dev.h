@@ -226,6 +226,7 @@ struct ZWaveArgs {
   const uint32_t* blk_lane;      // block -> lane inside its group
   int wave, chunk_bytes, ncs, ngroups;   // ncs = component slots per block = max components + 1 (coder)
   int gsize;                             // blocks per group (= active lanes of a component warp), <= 32
+  unsigned long long* prof;              // optional [32][2]: cycles and warp count per role (ZPQ_WAVE_PROF=1), else null
 };
 
 #endif

@@ -17,8 +17,8 @@ cudaError_t zpq_launch_code(const ZKernelArgs* a, int nblk, int decode, int sm_c
 int zpq_code2_static_smem(void);
 int zpq_dec6_static_smem(void);
 int zpq_dec6_ctrl_bytes(void);
-cudaError_t zpq_launch_dec6(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, unsigned long long sig, cudaStream_t st);
-cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st);
+cudaError_t zpq_launch_dec6(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, unsigned long long sig, int variant, cudaStream_t st);
+cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant);
 cudaError_t zpq_launch_enc4(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, cudaStream_t st);
 cudaError_t zpq_launch_enc3(const ZKernelArgs* a, int nblk, int sm_count, int warps, int pw_bytes, cudaStream_t st);
 unsigned long long zpq_code2_signature(const ZFast* F);

@@ -48,25 +48,26 @@ __device__ __forceinline__ void enc5_bit(Enc5& C, int y, u32 p16) {
 
 #define CS_WORDS 16     // per (block, component) state record, in u32
 
-__global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  stage_tables(smem, W.A.tables);
-  __syncthreads();
+// ROLE 0: component threads and MIX warps in one launch; 1: component threads only; 2: MIX warps only
+// (the split launches have their own register budgets).  Returns the profiling slot of the warp
+// (component type, 10 = coder, 11 + q = mixer q) or -1 for a warp without work in this wave.
+template <int ROLE, bool MIXPF>
+__device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem) {
   const Tabs S = make_tabs(smem);
   const ZKernelArgs& A = W.A;
 
   const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // global warp index
   const int CB = W.chunk_bytes, NCS = W.ncs;
   const int nA = W.ngroups * NCS;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) + (ROLE == 2 ? nA : 0);   // global warp index
 
-  if (gw < nA) {
+  if (ROLE != 2 && gw < nA) {
     // =======================================================================================
     // thread = (block, component) ; warp = one component of the 32 blocks of a group
     // =======================================================================================
     const int g = gw / NCS, c = gw - g * NCS;
     const int cnt = (int)W.group_count[g];
-    if (lane >= cnt) return;
+    if (lane >= cnt) return -1;
     const int bi = (int)W.group_first[g] + lane;
     const ZBlock B = A.blocks[bi];
     const ZModel* __restrict__ ZM = A.models + B.model;
@@ -83,9 +84,9 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     if (c == NCS - 1) {
       // ---------------- coder stage ----------------
       const int ch = W.wave - (int)ZM->wave.dcoder;
-      if (ch < 0) return;
+      if (ch < 0) return -1;
       const int b0 = ch * CB;
-      if (b0 >= N && !(ch == 0)) return;
+      if (b0 >= N && !(ch == 0)) return -1;
       const int b1 = min(N, b0 + CB);
       Enc5 C;
       C.out = A.out + B.out_off; C.out_cap = B.out_cap;
@@ -117,16 +118,16 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
       cs[0] = C.low; cs[1] = C.high; cs[2] = (u32)C.out_pos; cs[3] = (u32)(C.out_pos >> 32); cs[9] = (u32)C.status;
       cs[4] = seg; cs[5] = (u32)seg_end; cs[6] = (u32)(seg_end >> 32); cs[7] = (u32)seg_start_out; cs[8] = (u32)(seg_start_out >> 32);
       if (b1 >= N) { A.status[bi] = C.status; A.out_len[bi] = C.out_pos; }
-      return;
+      return 10;
     }
-    if (c >= n) return;
+    if (c >= n) return -1;
     const ZComp cd = ZM->comp[c];
     const u32 type = cd.type;
-    if (type == ZT_MIX) return;                                  // mixers have their own warps below
+    if (type == ZT_MIX) return -1;                                  // mixers have their own warps below
     const int ch = W.wave - (int)ZM->pipe.depth[c];
-    if (ch < 0) return;
+    if (ch < 0) return -1;
     const int b0 = ch * CB;
-    if (b0 >= N) return;
+    if (b0 >= N) return -1;
     const int b1 = min(N, b0 + CB);
     const int slot = ch & 15;
 
@@ -376,27 +377,27 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     cs[0] = h; cs[1] = st[0]; cs[2] = st[1]; cs[3] = st[2]; cs[4] = st[3];
     cs[5] = (u32)hist; cs[6] = (u32)(hist >> 32); cs[7] = dist_last;
     cs[8] = ma; cs[9] = mb; cs[10] = mpos; cs[11] = mpred;
-    return;
+    return (int)type;
   }
 
   // =========================================================================================
   // MIX warps: warp = (block, mixer); lane l = input l
   // =========================================================================================
-  {
+  if (ROLE != 1) {
     const int idx = gw - nA;
     const int bi = idx / ZPQ_FAST_MIX, q = idx - bi * ZPQ_FAST_MIX;
-    if (bi >= A.nblk) return;
+    if (bi >= A.nblk) return -1;
     const ZBlock B = A.blocks[bi];
     const ZModel* __restrict__ ZM = A.models + B.model;
-    if (q >= (int)ZM->team.nmix) return;
+    if (q >= (int)ZM->team.nmix) return -1;
     const int cq = (int)ZM->team.mix_comp[q];
     const ZComp cd = ZM->comp[cq];
     const int ch = W.wave - (int)ZM->pipe.depth[cq];
-    if (ch < 0) return;
+    if (ch < 0) return -1;
     int N = 0;
     for (u32 sg = 0; sg < B.nseg; ++sg) N += (int)A.seg_len[B.seg_first + sg];
     const int b0 = ch * CB;
-    if (b0 >= N) return;
+    if (b0 >= N) return -1;
     const int b1 = min(N, b0 + CB);
     const int slot = ch & 15;
     const u8* const in = A.in + B.in_off;
@@ -421,6 +422,63 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
     u32 cur_n = in[b0];
     uint4 vin_n = make_uint4(0, 0, 0, 0);
     if (lane < m) vin_n = pb[PBIDX2(j0 + lane, slot, 0)];
+    if (MIXPF && (a5 & 255u) == 255u && cmm >= 255u) {
+      // The eight weight rows of a byte are distinct (c8 takes eight different values under a full mask)
+      // and their indexes are input data: the rows of byte pos+1 are requested during bit 4 of byte pos,
+      // as soon as its context hash is known, so a warp has eight row loads in flight instead of one.
+      // A row of the next byte that is still to be trained in bits 4..7 of this byte ("late") is loaded
+      // at the start of its own byte instead, after the stores (same thread, program order).
+      int wr[8], wn[8];
+      u32 latem = 0xffu;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { wr[k] = 0; wn[k] = 0; }
+      for (int pos = b0; pos < b1; ++pos) {
+        const u32 cur = cur_n;
+        const int i = pos - b0;
+        const uint4 vin = vin_n;
+        const bool more = pos + 1 < b1;
+        if (more) {
+          cur_n = in[pos + 1];
+          if (lane < m) vin_n = pb[PBIDX2(j0 + lane, slot, i + 1)];
+        }
+        u32 bb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          bb[k] = ((h + (((0x100u | cur) >> (8 - k)) & a5)) & cmm) * (u32)m;
+          if ((latem >> k) & 1u) wr[k] = lane < m ? tab[bb[k] + lane] : 0;
+          else wr[k] = wn[k];
+        }
+        latem = 0xffu;
+        uint4 vout = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+          if (bit == 4) {
+            const u64 hs = (hist << 8) | (u64)cur;
+            h_next = flat_eval(fops, flen, st, cur, hs, pos, in, 0u);
+            hist = hs;
+            if (more) {
+              latem = 0u;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const u32 nb = ((h_next + (((0x100u | cur_n) >> (8 - k)) & a5)) & cmm) * (u32)m;
+                if (nb == bb[4] || nb == bb[5] || nb == bb[6] || nb == bb[7]) latem |= 1u << k;
+                else wn[k] = lane < m ? tab[nb + lane] : 0;
+              }
+            }
+          }
+          const int y = (int)((cur >> (7 - bit)) & 1u);
+          const int wc = wr[bit];
+          const int x = vget(vin, bit);
+          const int sum = __reduce_add_sync(FULL, lane < m ? (wc >> 8) * x : 0);
+          const int p = clamp2k(sum >> 8);
+          const int err = ((y * 32767 - t_squash(S, p)) * rate) >> 4;
+          if (lane < m) tab[bb[bit] + lane] = clamp512k(wc + ((err * x + (1 << 12)) >> 13));
+          vset(vout, bit, p);
+        }
+        if (lane == 0) pb[PBIDX2(cq, slot, i)] = vout;
+        h = h_next;
+      }
+    } else
     for (int pos = b0; pos < b1; ++pos) {
       const u32 cur = cur_n;
       const int i = pos - b0;
@@ -470,14 +528,39 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
       cs[0] = h; cs[1] = st[0]; cs[2] = st[1]; cs[3] = st[2]; cs[4] = st[3];
       cs[5] = (u32)hist; cs[6] = (u32)(hist >> 32);
     }
+    return 11 + q;
+  }
+  return -1;
+}
+
+template <int ROLE, bool MIXPF>
+__global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_tables(smem, W.A.tables);
+  __syncthreads();
+  const long long t0 = W.prof ? clock64() : 0;
+  const int slot = wave_body<ROLE, MIXPF>(W, smem);
+  if (W.prof && slot >= 0) {
+    if ((threadIdx.x & 31) == 0) { atomicAdd(W.prof + 2 * slot, (unsigned long long)(clock64() - t0)); atomicAdd(W.prof + 2 * slot + 1, 1ull); }
   }
 }
 
 // ---------------------------------------------------------------------------
-extern "C" cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st) {
-  const int warps = w->ngroups * w->ncs + w->A.nblk * ZPQ_FAST_MIX;
-  if (warps <= 0) return cudaSuccess;
-  const int ctas = (warps + 3) / 4;
-  zpq_wave_kernel<<<ctas, 128, S2_STATIC, st>>>(*w);
+extern "C" cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant) {
+  // variant bit 0: byte-ahead weight rows in the MIX warps; bit 1: component threads and MIX warps as two launches
+  const int wa = w->ngroups * w->ncs, wm = w->A.nblk * ZPQ_FAST_MIX;
+  if (wa + wm <= 0) return cudaSuccess;
+  const bool pf = (variant & 1) != 0;
+  if (variant & 2) {
+    if (wa > 0) zpq_wave_kernel<1, false><<<(wa + 3) / 4, 128, S2_STATIC, st>>>(*w);
+    if (wm > 0) {
+      if (pf) zpq_wave_kernel<2, true><<<(wm + 3) / 4, 128, S2_STATIC, st>>>(*w);
+      else zpq_wave_kernel<2, false><<<(wm + 3) / 4, 128, S2_STATIC, st>>>(*w);
+    }
+  } else {
+    const int ctas = (wa + wm + 3) / 4;
+    if (pf) zpq_wave_kernel<0, true><<<ctas, 128, S2_STATIC, st>>>(*w);
+    else zpq_wave_kernel<0, false><<<ctas, 128, S2_STATIC, st>>>(*w);
+  }
   return cudaGetLastError();
 }

@@ -49,7 +49,17 @@ __device__ __forceinline__ int dec6_bit(Dec6& C, u32 p16) {
   return y;
 }
 
-template <unsigned long long SIG>
+// steps of kind `kind` among the first `upto` steps of a signature: the weight / row register slot of a step
+__host__ __device__ constexpr int sig_count(unsigned long long sig, int upto, unsigned kind) {
+  int c = 0;
+  for (int s = 0; s < upto; ++s) if (((sig >> (3 * s)) & 7ull) == kind) ++c;
+  return c;
+}
+
+// V bit 0: CM / CONST components live in warp A, which requests both candidate entries of the next bit
+//          while it waits for the decoder;
+// V bit 1: warp B requests both candidate MIX / SSE rows of the next bit at the top of the current bit.
+template <unsigned long long SIG, int V>
 __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, const int pw_bytes, const int nteams) {
   extern __shared__ __align__(16) unsigned char smem[];
   {
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
     u32* gtab = nullptr; u8* ht = nullptr;
     if (lane < n) {
       const ZComp cd = ZM->comp[lane];
-      const bool hashc = cd.type == ZT_ICM || cd.type == ZT_ISSE;
+      const bool hashc = cd.type == ZT_ICM || cd.type == ZT_ISSE || ((V & 1) && (cd.type == ZT_CM || cd.type == ZT_CONS));
       if ((role == 0) == hashc) {
         type = cd.type; a1 = cd.a1; a2 = cd.a2; a3 = cd.a3; a4 = cd.a4; a5 = cd.a5;
         cm_mask = cd.cm_mask; ht_mask = cd.ht_mask; limit = cd.limit; level = ZM->fast.level[lane];
@@ -145,13 +155,20 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       // =================================== warp A: ICM / ISSE ===================================
       uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
       u32 bh = 0, v0 = 0, v1 = 0; int xj = 0;
+      u32 cxa = 0, cand0 = 0, cand1 = 0; bool cand = false; int ylast = 0;
+      const bool hashl = type == ZT_ICM || type == ZT_ISSE;
       const int nlev = (int)ZM->fast.nlev;
       bool abort = false;
       for (u32 sg = 0; sg < B.nseg && !abort; ++sg) {
         for (;;) {
           // ---- predict ----
           const bool nib = (c8 == 1) || ((c8 & 0xf0) == 16);
-          if (mine) {
+          if ((V & 1) && type == ZT_CM) {
+            cxa = (h ^ (u32)hmap4) & cm_mask;
+            v0 = cand ? (ylast ? cand1 : cand0) : gtab[cxa];
+            p = t_stretch(S, v0 >> 17);
+          }
+          if ((V & 1) ? hashl : mine) {
             if (nib) d_find(ht, ht_mask, (int)a1 + 2, h + 16u * (u32)c8, row, row_off);
             bh = row_get(row, hmap4 & 15);
             if (type == ZT_ISSE) {
@@ -174,6 +191,18 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           __threadfence_block();
           __syncwarp();
           if (lane == 0) *flagA = seq;
+          if ((V & 1) && type == ZT_CM) {
+            // both entries the next bit can use (hmap4 values of one byte are distinct and < 512)
+            cand = c8 < 128 && cm_mask >= 511u;
+            if (cand) {
+              u32 hm0;
+              if (c8 >= 8 && c8 < 16) hm0 = (u32)((hmap4 & 0xf) << 5 | 1);
+              else hm0 = (u32)((hmap4 & 0x1f0) | (((hmap4 & 0xf) * 2) & 0xf));
+              const u32 hm1 = hm0 | ((c8 >= 8 && c8 < 16) ? 16u : 1u);
+              cand0 = gtab[(h ^ hm0) & cm_mask];
+              cand1 = gtab[(h ^ hm1) & cm_mask];
+            }
+          }
           // ---- wait for the decoder ----
           u32 msg;
           while (((msg = *flagB) >> 3) != (seq & SEQ_MASK)) { }
@@ -184,7 +213,14 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           if (kind == 1u) break;                              // end of segment (the prediction above was not used)
           const int y = (int)(msg & 1u);
           // ---- update ----
-          if (mine) {
+          if ((V & 1) && type == ZT_CM) {
+            const u32 count = v0 & 0x3ffu;
+            const int err = y * 32767 - (int)(v0 >> 17);
+            const u32 prod = (u32)err * ((u32)S.dt[count] * 2u);
+            gtab[cxa] = v0 + (prod & 0xfffffc00u) + (count < limit ? 1u : 0u);
+            ylast = y;
+          }
+          if ((V & 1) ? hashl : mine) {
             const u32 nx = ((u32)S.ns[bh] >> (8 * y)) & 255u;
             row_set(row, hmap4 & 15, nx);
             if (type == ZT_ISSE) {
@@ -197,7 +233,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
             }
           }
           const int c8n = c8 * 2 + y;
-          if (mine && (c8n >= 256 || (c8n >= 16 && c8n < 32))) *reinterpret_cast<uint4*>(ht + row_off) = row;
+          if (((V & 1) ? hashl : mine) && (c8n >= 256 || (c8n >= 16 && c8n < 32))) *reinterpret_cast<uint4*>(ht + row_off) = row;
           if (c8n >= 256) BYTE_END(c8n - 256);
           else {
             c8 = c8n;
@@ -208,7 +244,9 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       }
     } else {
       // ================ warp B: CM, MATCH, CONST, AVG, MIX2, SSE, MIX, arithmetic decoder ================
-      const int nsteps = (int)ZM->fast.nsteps, nmix = (int)ZM->fast.nmix, nsse = (int)ZM->fast.nsse;
+      constexpr int NMIXC = SIG ? sig_count(SIG, ZPQ_FAST_STEPS, ZK_MIX) : ZPQ_FAST_MIX;     // known from the signature
+      constexpr int NSSEC = SIG ? sig_count(SIG, ZPQ_FAST_STEPS, ZK_SSE) : ZPQ_FAST_SSE;
+      const int nsteps = (int)ZM->fast.nsteps, nmix = SIG ? NMIXC : (int)ZM->fast.nmix, nsse = SIG ? NSSEC : (int)ZM->fast.nsse;
       u32 sd[ZPQ_FAST_STEPS];
 #pragma unroll
       for (int s = 0; s < ZPQ_FAST_STEPS; ++s) sd[s] = ZM->fast.sd[s];
@@ -227,6 +265,12 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       int mixw0 = 0, mixw1 = 0, mixw2 = 0, mixx0 = 0, mixx1 = 0, mixx2 = 0; u32 sserow0 = 0, sserow1 = 0;
       u32 cxt = 0, v0 = 0; int xj = 0, xk = 0;
       u32 ma = 0, mb = 0, mpos = 0, mbit = 0, mpred = 0, mc = 0;
+      // candidate rows of the next bit (V bit 1): valid when every MIX has a full c8 mask and >= 256 rows and
+      // every SSE has >= 256 rows, so that the two candidate rows differ from the row trained in this bit
+      int mc00 = 0, mc01 = 0, mc10 = 0, mc11 = 0, mc20 = 0, mc21 = 0; u32 sc00 = 0, sc01 = 0, sc10 = 0, sc11 = 0;
+      bool candv = false; int ylast = 0;
+      const bool cand_ok = (V & 2) && __all_sync(FULL, (type != ZT_MIX || ((a5 & 255u) == 255u && cm_mask >= 255u)) &&
+                                                       (type != ZT_SSE || cm_mask >= 256u * 32u - 1u));
 
       Dec6 C;
       C.low = 1; C.high = 0xffffffffu; C.curr = 0; C.status = ST_OK;
@@ -257,7 +301,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           bool failed = false;
           for (int bit = 7; bit >= 0; --bit) {
             // ---- own table lookups and early row fetches (overlap warp A's ISSE chain) ----
-            if (type == ZT_CM) {
+            if (!(V & 1) && type == ZT_CM) {
               cxt = (h ^ (u32)hmap4) & cm_mask;
               v0 = gtab[cxt];
               p = t_stretch(S, v0 >> 17);
@@ -273,22 +317,48 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
               cxt = (h + (u32)(c8 & (int)a5)) & cm_mask;
               v0 = reinterpret_cast<const u16*>(gtab)[cxt];
             }
-            else if (type == ZT_MIX) cxt = ((h + (u32)(c8 & (int)a5)) & cm_mask) * a3;
-            else if (type == ZT_SSE) cxt = ((h + (u32)c8) * 32u) & cm_mask;
+            // cxn0 / cxn1 = the row of the NEXT bit when this bit decodes to 0 / 1
+            u32 cxn0 = 0, cxn1 = 0;
+            if (type == ZT_MIX) {
+              cxt = ((h + (u32)(c8 & (int)a5)) & cm_mask) * a3;
+              if (V & 2) { cxn0 = ((h + (u32)((c8 * 2) & (int)a5)) & cm_mask) * a3; cxn1 = ((h + (u32)((c8 * 2 + 1) & (int)a5)) & cm_mask) * a3; }
+            }
+            else if (type == ZT_SSE) {
+              cxt = ((h + (u32)c8) * 32u) & cm_mask;
+              if (V & 2) { cxn0 = ((h + (u32)(c8 * 2)) * 32u) & cm_mask; cxn1 = ((h + (u32)(c8 * 2 + 1)) * 32u) & cm_mask; }
+            }
+            const bool use_cand = (V & 2) && candv;
+            candv = (V & 2) && cand_ok && c8 < 128;
 #pragma unroll
             for (int q = 0; q < ZPQ_FAST_MIX; ++q)
-              if (q < nmix) {
+              if (q < NMIXC && q < nmix) {
                 const u32 base = __shfl_sync(FULL, cxt, (int)mix_owner[q]);
                 mixbase[q] = base;
-                const int wq = lane < (int)mix_m[q] ? mix_tab[q][base + lane] : 0;
+                int wq;
+                if (use_cand) wq = q == 0 ? (ylast ? mc01 : mc00) : (q == 1 ? (ylast ? mc11 : mc10) : (ylast ? mc21 : mc20));
+                else wq = lane < (int)mix_m[q] ? mix_tab[q][base + lane] : 0;
                 if (q == 0) mixw0 = wq; else if (q == 1) mixw1 = wq; else mixw2 = wq;
+                if ((V & 2) && candv) {
+                  const u32 nb0 = __shfl_sync(FULL, cxn0, (int)mix_owner[q]), nb1 = __shfl_sync(FULL, cxn1, (int)mix_owner[q]);
+                  const int m_ = (int)mix_m[q];
+                  const int n0 = lane < m_ ? mix_tab[q][nb0 + lane] : 0;
+                  const int n1 = lane < m_ ? mix_tab[q][nb1 + lane] : 0;
+                  if (q == 0) { mc00 = n0; mc01 = n1; } else if (q == 1) { mc10 = n0; mc11 = n1; } else { mc20 = n0; mc21 = n1; }
+                }
               }
 #pragma unroll
             for (int r = 0; r < ZPQ_FAST_SSE; ++r)
-              if (r < nsse) {
+              if (r < NSSEC && r < nsse) {
                 const u32 rb = __shfl_sync(FULL, cxt, (int)sse_owner[r]);
-                const u32 rowv = sse_tab[r][rb + lane];
+                u32 rowv;
+                if (use_cand) rowv = r == 0 ? (ylast ? sc01 : sc00) : (ylast ? sc11 : sc10);
+                else rowv = sse_tab[r][rb + lane];
                 if (r == 0) sserow0 = rowv; else sserow1 = rowv;
+                if ((V & 2) && candv) {
+                  const u32 nb0 = __shfl_sync(FULL, cxn0, (int)sse_owner[r]), nb1 = __shfl_sync(FULL, cxn1, (int)sse_owner[r]);
+                  const u32 n0 = sse_tab[r][nb0 + lane], n1 = sse_tab[r][nb1 + lane];
+                  if (r == 0) { sc00 = n0; sc01 = n1; } else { sc10 = n0; sc11 = n1; }
+                }
               }
             if (type == ZT_CM || type == ZT_MATCH || type == ZT_CONS) pp[lane] = (short)p;
             // ---- predictions of the hash components ----
@@ -305,7 +375,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
                 const int owner = (int)((d >> 3) & 31u), sj = (int)((d >> 8) & 31u), sk = (int)((d >> 13) & 63u);
                 if (kind == ZK_ISSE) { /* done by warp A */ }
                 else if (kind == ZK_MIX) {
-                  const u32 q = d >> 27;
+                  const u32 q = SIG ? (u32)sig_count(SIG, s, ZK_MIX) : d >> 27;
                   const int x = (int)pp[(sj + lane) & 31];
                   const int w = q == 0 ? mixw0 : (q == 1 ? mixw1 : mixw2);
                   if (q == 0) mixx0 = x; else if (q == 1) mixx1 = x; else mixx2 = x;
@@ -328,7 +398,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
                   int pq = min(max(pj + 992, 0), 1983);
                   const int wt = pq & 63;
                   pq >>= 6;
-                  const u32 rowv = (d >> 27) == 0 ? sserow0 : sserow1;
+                  const u32 rowv = (SIG ? (u32)sig_count(SIG, s, ZK_SSE) : d >> 27) == 0 ? sserow0 : sserow1;
                   const u32 q0 = __shfl_sync(FULL, rowv, pq), q1 = __shfl_sync(FULL, rowv, pq + 1);
                   if (lane == owner) {
                     p = t_stretch(S, (u32)(((int)(q0 >> 10) * (64 - wt) + (int)(q1 >> 10) * wt) >> 13));
@@ -349,6 +419,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
             const int y = dec6_bit(C, (u32)t_squash(S, pfin) * 2u + 1u);
             if (C.status != ST_OK) { status = C.status; SEND(2, 0); failed = true; break; }
             SEND(0, y);
+            ylast = y;
             // ---- update own components ----
             if (type == ZT_CM || type == ZT_SSE) {
               const u32 count = v0 & 0x3ffu;
@@ -382,7 +453,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
             }
 #pragma unroll
             for (int q = 0; q < ZPQ_FAST_MIX; ++q)
-              if (q < nmix) {
+              if (q < NMIXC && q < nmix) {
                 const int e0 = ((y * 32767 - t_squash(S, p)) * (int)mix_rate[q]) >> 4;
                 const int err = __shfl_sync(FULL, e0, (int)mix_owner[q]);
                 const int w = q == 0 ? mixw0 : (q == 1 ? mixw1 : mixw2);
@@ -422,29 +493,39 @@ static const unsigned long long kSig6L4 = 1ull | 1ull << 3 | 1ull << 6 | 1ull <<
 static const unsigned long long kSig6L5 = 1ull | 1ull << 3 | 1ull << 6 | 1ull << 9 | 1ull << 12 | 1ull << 15 | 1ull << 18 |
                                           2ull << 21 | 2ull << 24 | 3ull << 27 | 4ull << 30 | 3ull << 33;
 
-template <unsigned long long SIG>
+template <unsigned long long SIG, int V>
 static cudaError_t launch6(const ZKernelArgs* a, int ctas, int threads, size_t smem, int pw_bytes, int teams, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(zpq_dec_kernel6<SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(zpq_dec_kernel6<SIG, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZPQ_SMEM_MAX);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  zpq_dec_kernel6<SIG><<<ctas, threads, smem, st>>>(*a, pw_bytes, teams);
+  zpq_dec_kernel6<SIG, V><<<ctas, threads, smem, st>>>(*a, pw_bytes, teams);
   return cudaGetLastError();
 }
 
 extern "C" int zpq_dec6_static_smem(void) { return S6_STATIC; }
 extern "C" int zpq_dec6_ctrl_bytes(void) { return S6_CTRL; }
 
+template <int V>
+static cudaError_t launch6v(const ZKernelArgs* a, int ctas, int th, size_t smem, int pw_bytes, int teams, unsigned long long sig, cudaStream_t st) {
+  if (sig == kSig6L5) return launch6<kSig6L5, V>(a, ctas, th, smem, pw_bytes, teams, st);
+  if (sig == kSig6L4) return launch6<kSig6L4, V>(a, ctas, th, smem, pw_bytes, teams, st);
+  return launch6<0ull, V>(a, ctas, th, smem, pw_bytes, teams, st);
+}
+
 extern "C" cudaError_t zpq_launch_dec6(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes,
-                                       unsigned long long sig, cudaStream_t st) {
+                                       unsigned long long sig, int variant, cudaStream_t st) {
   if (nblk <= 0) return cudaSuccess;
   const size_t smem = (size_t)S6_STATIC + (size_t)teams * (pw_bytes + S6_CTRL);
   int ctas = (nblk + teams - 1) / teams;
   if (ctas > sm_count) ctas = sm_count;
   const int th = teams * 64;
-  if (sig == kSig6L5) return launch6<kSig6L5>(a, ctas, th, smem, pw_bytes, teams, st);
-  if (sig == kSig6L4) return launch6<kSig6L4>(a, ctas, th, smem, pw_bytes, teams, st);
-  return launch6<0ull>(a, ctas, th, smem, pw_bytes, teams, st);
+  switch (variant & 3) {
+    case 1: return launch6v<1>(a, ctas, th, smem, pw_bytes, teams, sig, st);
+    case 2: return launch6v<2>(a, ctas, th, smem, pw_bytes, teams, sig, st);
+    case 3: return launch6v<3>(a, ctas, th, smem, pw_bytes, teams, sig, st);
+    default: return launch6v<0>(a, ctas, th, smem, pw_bytes, teams, sig, st);
+  }
 }
