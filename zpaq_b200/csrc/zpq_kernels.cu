@@ -133,10 +133,9 @@ __device__ __forceinline__ void d_find(u8* ht, u32 ht_mask, int shift, u32 cxt, 
 }
 
 // ---------------------------------------------------------------------------
-// HCOMP interpreter (ZPAQL::run0/execute, libzpaq.cpp:1027-1262).  Executed
-// uniformly by the whole warp: every lane holds the same a,b,c,d,f,pc and
-// issues the same loads/stores (same address, same value), so no intra-warp
-// synchronisation is needed and lane i can read H[i] afterwards.
+// HCOMP interpreter (ZPAQL::run0/execute, libzpaq.cpp:1027-1262).  Run by lane 0
+// of the block's warp (the call sites follow it with __syncwarp, after which
+// lane i reads H[i]); the machine registers a,b,c,d,f live in that lane.
 // `code` points at the first program byte inside an image with zero guards on
 // both sides, so runaway jumps fetch opcode 0 = error exactly as the
 // reference's guard gaps do (libzpaq.cpp:913).
@@ -593,7 +592,12 @@ __global__ void __launch_bounds__(ZPQ_WARPS * 32, 2) zpq_code_kernel(const ZKern
             if (L.type == ZT_ICM || L.type == ZT_ISSE) *reinterpret_cast<uint4*>(L.ht + L.row_off) = L.row;
           }
           if (c8n >= 256) {
-            const int rc = vm_run(V, (u32)(c8n - 256));
+            // lane 0 interprets the program (every lane would issue the same loads and stores; running it once does not
+            // lean on lock-step execution), __syncwarp orders its H[] stores before the reads below
+            int rc = ST_OK;
+            if (lane == 0) rc = vm_run(V, (u32)(c8n - 256));
+            __syncwarp();
+            rc = __shfl_sync(FULL, rc, 0);
             if (rc != ST_OK) { status = rc; break; }
             M.hmap4 = 1; M.c8 = 1;
             L.h = V.h[(u32)lane & V.hmask];

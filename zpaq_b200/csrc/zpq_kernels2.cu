@@ -569,7 +569,10 @@ __global__ void __launch_bounds__(256, 1) zpq_code_kernel2(const ZKernelArgs A, 
           if (c8n >= 256) {
             if (use_rcp) L.h = hcomp_recipes(R, L.h, (u32)(c8n - 256), vm_c, hist, V.m, V.mmask, V.h, V.hmask);
             else {
-              const int rc = vm2_run(V, (u32)(c8n - 256));
+              int rc = ST_OK;                      // lane 0 interprets, see zpq_kernels.cu
+              if (lane == 0) rc = vm2_run(V, (u32)(c8n - 256));
+              __syncwarp();
+              rc = __shfl_sync(FULL, rc, 0);
               if (rc != ST_OK) { status = rc; break; }
               L.h = V.h[(u32)lane & V.hmask];
             }

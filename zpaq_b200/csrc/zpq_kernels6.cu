@@ -278,6 +278,10 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       C.out = A.out + B.out_off; C.out_pos = 0; C.out_cap = B.out_cap;
 
 #define SEND(kind, y) do { __threadfence_block(); __syncwarp(); if (lane == 0) *flagB = (seq & SEQ_MASK) << 3 | (u32)(kind) << 1 | (u32)(y); seq = (seq + 1) & SEQ_MASK; } while (0)
+// Control messages (end of segment, abort) leave the per-bit hand-shake: flagB is a one-word mailbox, so before it is
+// overwritten warp A must have consumed the previous message -- which it has once it published the prediction it is about
+// to wait on (flagA == seq).
+#define SEND_CTRL(kind) do { while (*flagA != seq) { } SEND(kind, 0); } while (0)
 
       for (u32 sg = 0; sg < B.nseg && status == ST_OK; ++sg) {
         const u64 seg_n = A.seg_len[B.seg_first + sg];
@@ -288,13 +292,13 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           if (C.in_pos >= C.in_end) { status = ST_EOF; break; }
           C.curr = C.curr << 8 | (u32)C.in[C.in_pos++];
         }
-        if (status != ST_OK) { SEND(2, 0); break; }
+        if (status != ST_OK) { SEND_CTRL(2); break; }
         for (;;) {
           const int eos = dec6_bit(C, 0);
-          if (C.status != ST_OK) { status = C.status; SEND(2, 0); break; }
+          if (C.status != ST_OK) { status = C.status; SEND_CTRL(2); break; }
           if (eos) {
-            if (C.curr != 0) { status = ST_EOS; SEND(2, 0); }
-            else SEND(1, 0);
+            if (C.curr != 0) { status = ST_EOS; SEND_CTRL(2); }
+            else SEND_CTRL(1);
             break;
           }
           int cbyte = 0;
@@ -474,8 +478,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           ++C.out_pos;
           if (status != ST_OK) {
             // warp A is about to publish the first bit of the next byte: consume it and stop the block
-            while (*flagA != seq) { }
-            SEND(2, 0);
+            SEND_CTRL(2);
             break;
           }
         }
