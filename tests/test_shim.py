@@ -10,6 +10,7 @@ from util import ROOT
 
 B200 = os.path.join(ROOT, "oracle", "_ref", "zpaq_b200")
 REF = os.path.join(ROOT, "oracle", "_ref", "zpaq_ref")
+STREAM = os.path.join(ROOT, "oracle", "_ref", "shim_stream")
 need_cli = pytest.mark.skipif(not (os.path.exists(B200) and os.path.exists(REF)), reason="CLI binaries not built (make -C oracle cli)")
 
 
@@ -22,8 +23,11 @@ def _files(tmp_path):
     return names
 
 
-def _run(exe, args, cwd):
-    r = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+def _run(exe, args, cwd, log=False):
+    env = dict(os.environ)
+    if log:
+        env["ZPQ_SHIM_LOG"] = "1"       # one stderr line per routed call: proves which path ran
+    r = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=900, env=env)
     return r.returncode, r.stdout + r.stderr
 
 
@@ -54,3 +58,56 @@ def test_zpaq_add_on_gpu_extracts_with_stock_zpaq(tmp_path, method):
     rc, out = _run(REF, ["add", "r.zpaq"] + names + ["-method", method, "-threads", "8"], tmp_path)
     assert rc == 0, out
     assert abs((tmp_path / "g.zpaq").stat().st_size - (tmp_path / "r.zpaq").stat().st_size) <= 64
+
+
+@need_cli
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["5", "3"])
+def test_zpaq_extract_on_gpu(tmp_path, method):
+    """`zpaq x` through the shim's Decompresser::decompress: archives written by the STOCK CLI are decoded by the GPU
+    library (method 5: context mixing; method 3: BWT, whose two-component model is decoded on the GPU and whose PCOMP
+    inverse transform stays the reference's PostProcessor)."""
+    names = _files(tmp_path)
+    rc, out = _run(REF, ["add", "s.zpaq"] + names + ["-method", method, "-threads", "4"], tmp_path)
+    assert rc == 0, out
+    rc, out = _run(B200, ["x", "s.zpaq", "-to", "ox", "-threads", "4"], tmp_path, log=True)
+    assert rc == 0, out
+    assert "components -> GPU" in out and "status 0" in out, out
+    for n in names:
+        assert (tmp_path / "ox" / n).read_bytes() == (tmp_path / n).read_bytes()
+
+
+@pytest.mark.skipif(not os.path.exists(STREAM), reason="stream driver not built (make -C oracle cli)")
+def test_stream_api_lz77_stays_on_the_cpu_code(tmp_path):
+    """libzpaq::compress / decompress through the shim with a method outside the context-model family: no GPU needed."""
+    data = O.gen_block(0, 31, 300000)
+    (tmp_path / "in").write_bytes(data)
+    rc, out = _run(STREAM, ["c", "1", "in", "a.zpaq"], tmp_path, log=True)
+    assert rc == 0, out
+    assert "0 of them -> GPU" in out, out
+    rc, out = _run(STREAM, ["d", "-", "a.zpaq", "out"], tmp_path, log=True)
+    assert rc == 0, out
+    assert (tmp_path / "out").read_bytes() == data
+
+
+@pytest.mark.skipif(not os.path.exists(STREAM), reason="stream driver not built (make -C oracle cli)")
+@pytest.mark.gpu
+def test_stream_api_through_the_gpu_library(tmp_path):
+    """libzpaq::compress(in, out, "50") reads its 1 MiB-class blocks ahead and codes them as one GPU batch; the archive
+    equals the reference's block for block, and libzpaq::decompress decodes it in one batch."""
+    import refpy
+    bs = (1 << 20) - 4096
+    data = O.gen_block(1, 5, 2 * bs + 123456)
+    (tmp_path / "in").write_bytes(data)
+    rc, out = _run(STREAM, ["c", "50", "in", "a.zpaq"], tmp_path, log=True)
+    assert rc == 0, out
+    assert "3 blocks" in out and "3 of them -> GPU" in out, out
+    got = (tmp_path / "a.zpaq").read_bytes()
+    if refpy.available():
+        want = b"".join(refpy.compress_block(data[i:i + bs], "50", b"name" if i == 0 else None, b"comment" if i == 0 else None)
+                        for i in range(0, len(data), bs))
+        assert got == want
+    rc, out = _run(STREAM, ["d", "-", "a.zpaq", "out"], tmp_path, log=True)
+    assert rc == 0, out
+    assert "-> GPU batch, status 0" in out, out
+    assert (tmp_path / "out").read_bytes() == data

@@ -88,8 +88,16 @@ def main():
     if bad:
         raise SystemExit("compile failed: " + " ".join(bad[0]))
     lib = os.path.join(OUT, "libzpq_simt.so")
-    subprocess.check_call(["g++", "-shared", "-o", lib] + objs + ["-lpthread"])
+    subprocess.check_call(["g++", "-shared", "-o", lib + ".new"] + objs + ["-lpthread"])
+    os.replace(lib + ".new", lib)          # a process that has the old build loaded keeps its mapping
     print("built", lib)
+    # the unchanged zpaq.cpp + the shim, linked against the emulator build instead of the CUDA build (objects from `make -C oracle cli`)
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    need = [os.path.join(ref, f) for f in ("zpaq.o", "libzpaq_shim.o", "libzpaq_renamed.o")]
+    if all(os.path.exists(f) for f in need):
+        exe = os.path.join(OUT, "zpaq_simt")
+        subprocess.check_call(["g++", "-pthread", "-o", exe] + need + ["-L", OUT, "-lzpq_simt", "-Wl,-rpath," + OUT])
+        print("built", exe)
 
 
 if __name__ == "__main__":
