@@ -32,3 +32,30 @@ def test_method_parity(kctx, method, kind):
         hdrs.setdefault(Z.model_from_method(method, p), []).append(p)
     for hdr, ps in hdrs.items():
         _roundtrip(ctx, hdr, ps)
+
+
+@pytest.mark.parametrize("env,values", [("ZPQ_DEC_VARIANT", ["0", "1", "2", "3", "7"]), ("ZPQ_WAVE_VARIANT", ["0", "1", "2", "3"])])
+def test_kernel_variants_are_bit_exact(env, values):
+    """Every switchable variant of the production kernels (two-warp decoder: candidate entries / rows, slot-scheduled
+    hashes; wavefront encoder: byte-ahead MIX rows, split launches) codes the same bytes as the oracle."""
+    import os
+    payloads = [O.gen_block(kind, 500 + kind, 6000 + 111 * kind) for kind in (0, 1, 2, 3)]
+    for v in values:
+        old = os.environ.get(env)
+        os.environ[env] = v
+        try:
+            ctx = Z.Context(0)
+        finally:
+            if old is None:
+                del os.environ[env]
+            else:
+                os.environ[env] = old
+        try:
+            for method in ("4", "5", CFG_ALL_METHOD):
+                hdrs = {}
+                for p in payloads:
+                    hdrs.setdefault(Z.model_from_method(method, p), []).append(p)
+                for hdr, ps in hdrs.items():
+                    _roundtrip(ctx, hdr, ps)
+        finally:
+            ctx.close()

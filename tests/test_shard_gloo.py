@@ -35,8 +35,15 @@ def _worker(rank, world, port, q):
     mine = [_code(p) for p in pays[lo:hi]]
     allb = shard.gather_blocks(mine, dst=0)
     t = shard.max_over_ranks(1.0 + rank)
+    # the tensor path: raw blocks scattered from rank 0 (only rank 0 holds them), coded, coded bytes gathered back
+    first, got = shard.scatter_blocks(pays if rank == 0 else None, src=0)
+    assert first == lo and [bytes(t.numpy().tobytes()) for t in got] == pays[lo:hi]
+    coded = shard.gather_segments([_code(bytes(t.numpy().tobytes())) for t in got], dst=0)
     if rank == 0:
+        assert coded == allb
         q.put((b"".join(allb), t))
+    else:
+        assert coded is None
     dist.barrier()
     dist.destroy_process_group()
 

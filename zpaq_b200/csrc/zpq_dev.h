@@ -133,6 +133,25 @@ struct ZWave {
   alignas(16) uint32_t flat[ZPQ_MAX_LANES][ZPQ_FLAT_MAX];   // rows of 160 bytes, fetched 16 bytes at a time
 };
 
+// Slot-scheduled context hashes (two-warp decoder, zpq_kernels6.cu).  In the decoder a lane is a component, so the
+// flattened recipes of a warp's lanes are DIFFERENT programs and interpreting them lane by lane diverges on every op.
+// The host merges the op lists of all lanes into one sequence of slots whose op kind is the same for every lane
+// (a shortest-common-supersequence heuristic, zpq_hcomp.cpp build_hash_plan); a lane that has no op in a slot sits it
+// out.  Evaluation is then one uniform loop: slot[s].kind picks the code, w[s][lane] is the lane's operand word,
+// slot[s].lanes the participants.  Host-verified against the flat form.
+#define ZPQ_HSLOTS 28
+// slot kinds: the flat ops, with the two folding ops split by where their operand comes from so that the common case
+// (one of the last eight bytes, held in a register) is straight-line code
+enum { ZH_SEG = 1, ZH_FOLD_BYTE, ZH_FOLD_OTHER, ZH_SHL8_BYTE, ZH_SHL8_OTHER, ZH_SHR, ZH_SHL, ZH_ROLL, ZH_WORD };
+struct ZHashSlot { uint32_t lanes, kind; };   // lanes that have an op in the slot; ZH_*
+struct ZHashPlan {
+  uint32_t ok, nslots;
+  uint8_t last_seg[ZPQ_MAX_LANES];       // index of the lane's last segment (its state receives the final value)
+  alignas(8) ZHashSlot slot[ZPQ_HSLOTS];
+  uint32_t w[ZPQ_HSLOTS][32];            // operand word per lane (the flat op word; ZH_SEG: segment index in bits 8-9)
+  uint32_t w2[ZPQ_HSLOTS][32];           // ZH_WORD: second word (multiplier, first flag)
+};
+
 // Team plan (zpq_kernels4.cu): the skewed pipeline of ZPipe split over THREE warps per block so that
 // the block's instruction stream is issued by three schedulers at once:
 //   role 0 = every ICM / ISSE component (one code path, no divergence)
@@ -175,6 +194,8 @@ struct ZModel {
   // ---- wavefront encode plan (zpq_kernels5.cu) ----
   ZWave wave;
   ZRecipes rcp;
+  // ---- slot-scheduled hashes for the two-warp decoder (zpq_kernels6.cu) ----
+  ZHashPlan hplan;
 };
 
 struct ZBlock {

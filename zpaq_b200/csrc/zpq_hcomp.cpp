@@ -427,4 +427,125 @@ void build_wave_plan(ZModel* M) {
   W.ok = 1;
 }
 
+
+// ---------------------------------------------------------------------------
+// Slot-scheduled hashes (ZHashPlan, zpq_dev.h): merge the flat op lists of all lanes into one sequence of
+// slots with a warp-uniform op kind.  Greedy: the next slot takes the kind that is the pending op of the most
+// lanes (ties: the smaller ZH_* value), every lane whose pending op has that kind advances.  The result is
+// checked against FlatEval on the same byte stream before it is marked usable.
+namespace {
+struct PlanEval {      // host mirror of hplan_eval (zpq_kcommon.cuh)
+  uint32_t st[32][ZPQ_FLAT_SEGS];
+  uint32_t dist_last[32]; uint32_t c; uint64_t hist;
+  std::vector<uint8_t> in;
+  PlanEval() { memset(st, 0, sizeof(st)); memset(dist_last, 0, sizeof(dist_last)); c = 0; hist = 0; }
+  void step(const ZHashPlan& P, int n, uint32_t byte, const uint8_t* dist_byte, uint32_t h[32]) {
+    --c; in.push_back((uint8_t)byte);
+    const long long bpos = (long long)in.size() - 1;
+    hist = (hist << 8) | byte;
+    uint32_t acc[32] = {0}, prev_new[32] = {0}, prev_old[32] = {0};
+    for (int l = 0; l < n; ++l) if (byte == dist_byte[l]) dist_last[l] = c;
+    for (uint32_t s = 0; s < P.nslots; ++s)
+      for (int l = 0; l < n; ++l) {
+        if (!((P.slot[s].lanes >> l) & 1u)) continue;
+        const uint32_t kind = P.slot[s].kind;
+        const uint32_t w = P.w[s][l], src = (w >> 4) & 15, arg = (w >> 8) & 255, off = w >> 16;
+        uint32_t x = 0;
+        if (kind == ZH_FOLD_BYTE || kind == ZH_SHL8_BYTE) x = (uint32_t)(hist >> (8 * off)) & arg;
+        else if (kind == ZH_FOLD_OTHER || kind == ZH_SHL8_OTHER) {
+          if (src == ZS_BYTE) x = (long long)off <= bpos ? (in[bpos - off] & arg) : 0;
+          else if (src == ZS_POSAND) x = c & arg;
+          else if (src == ZS_POSMOD) x = arg ? c % arg : 0;
+          else if (src == ZS_DIST) { x = dist_last[l] - c; if (x > 255) x = 255; }
+        }
+        switch (kind) {
+          case ZH_SEG: {
+            const uint32_t k = (w >> 8) & 3u;
+            if (k > 0) { prev_old[l] = st[l][k - 1]; st[l][k - 1] = acc[l]; prev_new[l] = acc[l]; }
+            acc[l] = src == ZB_ZERO ? 0 : (src == ZB_OWN ? st[l][k] : prev_new[l]);
+            break;
+          }
+          case ZH_FOLD_BYTE: case ZH_FOLD_OTHER: acc[l] = (acc[l] + x + 512) * 773; break;
+          case ZH_SHL8_BYTE: case ZH_SHL8_OTHER: acc[l] = (acc[l] << 8) + x; break;
+          case ZH_SHR: acc[l] >>= arg; break;
+          case ZH_SHL: acc[l] <<= arg; break;
+          case ZH_ROLL: acc[l] = acc[l] * off + byte + 1; break;
+          case ZH_WORD: {
+            const uint32_t w2 = P.w2[s][l];
+            const uint32_t v2 = off & 255, v3 = off >> 8, mult = w2 & 255, first = (w2 >> 8) & 1;
+            if ((((byte & arg) - v2) & 255) < v3) acc[l] = acc[l] * mult + byte + 1;
+            else acc[l] = first ? 0 : prev_old[l];
+            break;
+          }
+          default: break;
+        }
+      }
+    for (int l = 0; l < n; ++l) { st[l][P.last_seg[l]] = acc[l]; h[l] = acc[l]; }
+  }
+};
+}  // namespace
+
+void build_hash_plan(ZModel* M) {
+  ZHashPlan& P = M->hplan;
+  memset(&P, 0, sizeof(P));
+  const ZWave& W = M->wave;
+  if (!W.ok) return;
+  const int n = (int)M->n;
+  // per lane: the op list with ZR_WORD's second word folded into its op and segment indexes made explicit
+  struct Op { uint32_t kind, w, w2; };
+  std::vector<std::vector<Op>> ops(n);
+  for (int l = 0; l < n; ++l) {
+    int k = -1;
+    for (uint32_t t = 0; t < W.flat_len[l]; ++t) {
+      const uint32_t w = W.flat[l][t], kind = w & 15u;
+      if (kind == ZR_END) break;
+      const uint32_t src = (w >> 4) & 15u, off = w >> 16;
+      const bool reg_byte = src == ZS_BYTE && off < 8;        // one of the last eight bytes: in the history register
+      if (kind == ZR_SEG) { ++k; ops[l].push_back(Op{ZH_SEG, (w & 0xffu) | (uint32_t)k << 8, 0}); }
+      else if (kind == ZR_WORD) { ops[l].push_back(Op{ZH_WORD, w, W.flat[l][t + 1]}); ++t; }
+      else if (kind == ZR_FOLD) ops[l].push_back(Op{reg_byte ? (uint32_t)ZH_FOLD_BYTE : (uint32_t)ZH_FOLD_OTHER, w, 0});
+      else if (kind == ZR_SHL8ADD) ops[l].push_back(Op{reg_byte ? (uint32_t)ZH_SHL8_BYTE : (uint32_t)ZH_SHL8_OTHER, w, 0});
+      else if (kind == ZR_SHR) ops[l].push_back(Op{ZH_SHR, w, 0});
+      else if (kind == ZR_SHL) ops[l].push_back(Op{ZH_SHL, w, 0});
+      else if (kind == ZR_ROLL) ops[l].push_back(Op{ZH_ROLL, w, 0});
+      else return;                                  // an op this evaluator does not know
+    }
+    if (k < 0 || ops[l].empty() || ops[l][0].kind != ZH_SEG) return;
+    P.last_seg[l] = (uint8_t)k;
+  }
+  std::vector<size_t> at(n, 0);
+  uint32_t ns = 0;
+  for (;;) {
+    int count[16] = {0};
+    bool any = false;
+    for (int l = 0; l < n; ++l) if (at[l] < ops[l].size()) { ++count[ops[l][at[l]].kind]; any = true; }
+    if (!any) break;
+    int best = -1;
+    for (int kd = 0; kd < 16; ++kd) if (count[kd] > 0 && (best < 0 || count[kd] > count[best])) best = kd;
+    if (ns >= ZPQ_HSLOTS) return;
+    P.slot[ns].kind = (uint32_t)best;
+    for (int l = 0; l < n; ++l)
+      if (at[l] < ops[l].size() && (int)ops[l][at[l]].kind == best) {
+        P.slot[ns].lanes |= 1u << l; P.w[ns][l] = ops[l][at[l]].w; P.w2[ns][l] = ops[l][at[l]].w2; ++at[l];
+      }
+    ++ns;
+  }
+  P.nslots = ns;
+  // self-check against the flat form (which build_wave_plan checked against the recipes, which build_recipes
+  // checked against the bytecode)
+  std::vector<FlatEval> fe(n);
+  PlanEval pe;
+  uint32_t s = 977;
+  for (int i = 0; i < 4000; ++i) {
+    s = s * 1664525u + 1013904223u;
+    uint32_t byte = s >> 24;
+    if ((i / 400) & 1) byte = "the quick\nbrown fox jumps over\n"[(s >> 24) % 31];
+    uint32_t h[32];
+    pe.step(P, n, byte, M->pipe.dist_byte, h);
+    for (int l = 0; l < n; ++l)
+      if (fe[l].step(W.flat[l], W.flat_len[l], byte, M->pipe.dist_byte[l]) != h[l]) return;
+  }
+  P.ok = 1;
+}
+
 }  // namespace zpq

@@ -153,6 +153,74 @@ __device__ __forceinline__ u32 flat_eval(const u32* __restrict__ ops, u32 len, u
 }
 
 
+// Slot-scheduled hashes (ZHashPlan, zpq_dev.h): the recipes of all lanes as ONE sequence of slots with a warp-uniform op
+// kind, so the loop below has no per-lane control flow apart from the rare byte sources older than 8 bytes and the
+// position-modulo source.  `mine_mask` = lanes of this warp that own a component (slots without any of them are skipped),
+// `vc` = the HCOMP byte counter (0 - bytes seen), `ring` = the M ring the bytecode reads old bytes from.
+// Returns the lane's new hash (h_old for a lane that owns nothing).
+__device__ __forceinline__ u32 hplan_eval(const ZHashPlan* __restrict__ P, u32 mine_mask, int lane, u32 last_seg,
+                                          u32 st[ZPQ_FLAT_SEGS], u32 cur, u64 hs, u32 vc, const u8* ring, u32 ring_mask,
+                                          u32 dist_last, u32 h_old) {
+  u32 acc = 0, prev_new = 0, prev_old = 0;
+  const int ns = (int)P->nslots;
+  const uint2* __restrict__ sd = reinterpret_cast<const uint2*>(P->slot);
+  const u32* __restrict__ wp = &P->w[0][lane];
+  uint2 dn = __ldg(sd);
+  u32 wn = __ldg(wp);
+  for (int s = 0; s < ns; ++s) {
+    const u32 lm = dn.x, kind = dn.y, w = wn;
+    if (s + 1 < ns) { dn = __ldg(sd + s + 1); wn = __ldg(wp + (s + 1) * 32); }     // next slot requested one slot early
+    if (!(lm & mine_mask)) continue;                      // warp-uniform
+    const bool on = (lm >> lane) & 1u;
+    const u32 src = (w >> 4) & 15u, arg = (w >> 8) & 255u, off = w >> 16;
+    if (kind == ZH_FOLD_BYTE) {
+      const u32 x = (u32)(hs >> ((off & 7u) * 8u)) & arg;
+      if (on) acc = (acc + x + 512u) * 773u;
+    }
+    else if (kind == ZH_SEG) {
+      const u32 k = arg & 3u;
+      if (on) {
+        if (k > 0u) {
+          const u32 old = k == 1u ? st[0] : (k == 2u ? st[1] : st[2]);
+          if (k == 1u) st[0] = acc; else if (k == 2u) st[1] = acc; else st[2] = acc;
+          prev_old = old; prev_new = acc;
+        }
+        const u32 own = k == 0u ? st[0] : (k == 1u ? st[1] : (k == 2u ? st[2] : st[3]));
+        acc = src == ZB_ZERO ? 0u : (src == ZB_OWN ? own : prev_new);
+      }
+    }
+    else if (kind == ZH_SHL8_BYTE) {
+      const u32 x = (u32)(hs >> ((off & 7u) * 8u)) & arg;
+      if (on) acc = (acc << 8) + x;
+    }
+    else if (kind == ZH_FOLD_OTHER || kind == ZH_SHL8_OTHER) {
+      if (on) {
+        u32 x = 0;
+        if (src == ZS_BYTE) x = (u32)ring[(vc + off) & ring_mask] & arg;      // older than eight bytes: from the M ring
+        else if (src == ZS_POSAND) x = vc & arg;
+        else if (src == ZS_POSMOD) x = arg ? vc % arg : 0u;
+        else if (src == ZS_DIST) x = min(dist_last - vc, 255u);
+        acc = kind == ZH_FOLD_OTHER ? (acc + x + 512u) * 773u : (acc << 8) + x;
+      }
+    }
+    else if (kind == ZH_SHR) { if (on) acc >>= arg; }
+    else if (kind == ZH_SHL) { if (on) acc <<= arg; }
+    else if (kind == ZH_ROLL) { if (on) acc = acc * off + cur + 1u; }
+    else if (kind == ZH_WORD) {
+      const u32 w2 = __ldg(&P->w2[s][lane]);
+      const u32 v2 = off & 255u, v3 = off >> 8, mult = w2 & 255u, first = (w2 >> 8) & 1u;
+      if (on) {
+        if ((((cur & arg) - v2) & 255u) < v3) acc = acc * mult + cur + 1u;
+        else acc = first ? 0u : prev_old;
+      }
+    }
+  }
+  if (!((mine_mask >> lane) & 1u)) return h_old;
+  if (last_seg == 0u) st[0] = acc; else if (last_seg == 1u) st[1] = acc; else if (last_seg == 2u) st[2] = acc; else st[3] = acc;
+  return acc;
+}
+
+
 // Stage the CTA-wide tables into shared memory (call with all threads, then __syncthreads()).
 __device__ __forceinline__ void stage_tables(unsigned char* smem, const ZTables* T) {
   const uint4* src = reinterpret_cast<const uint4*>(T->stretch_hi);

@@ -58,7 +58,8 @@ __host__ __device__ constexpr int sig_count(unsigned long long sig, int upto, un
 
 // V bit 0: CM / CONST components live in warp A, which requests both candidate entries of the next bit
 //          while it waits for the decoder;
-// V bit 1: warp B requests both candidate MIX / SSE rows of the next bit at the top of the current bit.
+// V bit 1: warp B requests both candidate MIX / SSE rows of the next bit at the top of the current bit;
+// V bit 2: context hashes from the slot-scheduled plan (ZHashPlan) instead of lane-by-lane interpretation.
 template <unsigned long long SIG, int V>
 __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, const int pw_bytes, const int nteams) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -112,6 +113,11 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       }
     }
     const bool mine = type != ZT_NONE;
+    // context hashes: V bit 2 = slot-scheduled plan (zpq_hcomp.cpp build_hash_plan; the host only picks this
+    // instantiation when every model of the launch has one), else the flat recipes
+    const ZHashPlan* __restrict__ HP = &ZM->hplan;
+    const u32 mine_mask = __ballot_sync(FULL, mine);
+    const u32 hp_last = (lane < n) ? (u32)HP->last_seg[lane] : 0u;
     const u32 tabw = wbase + ((lane < n) ? ZM->fast.smem_off[lane] : 0u) / 4u;
     if (role == 0) {
       if (type == ZT_ICM || type == ZT_ISSE) { /* tables initialised below by the whole warp */ }
@@ -144,10 +150,9 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       const u32 bv_ = (u32)(byteval);                                                                \
       vm_c -= 1; mring[vm_c & mmask] = (u8)bv_;          /* both warps write the same value */       \
       hist = (hist << 8) | (u64)bv_;                                                                 \
-      if (mine) {                                                                                    \
-        if (bv_ == dist_byte) dist_last = vm_c;                                                      \
-        h = flat_eval(fops, flen, st, bv_, hist, (int)(0u - vm_c) - 1, mring, dist_last, mmask); \
-      }                                                                                              \
+      if (mine && bv_ == dist_byte) dist_last = vm_c;                                                \
+      if (V & 4) h = hplan_eval(HP, mine_mask, lane, hp_last, st, bv_, hist, vm_c, mring, mmask, dist_last, h);   \
+      else if (mine) h = flat_eval(fops, flen, st, bv_, hist, (int)(0u - vm_c) - 1, mring, dist_last, mmask);     \
       hmap4 = 1; c8 = 1;                                                                             \
     } while (0)
 
@@ -525,10 +530,11 @@ extern "C" cudaError_t zpq_launch_dec6(const ZKernelArgs* a, int nblk, int sm_co
   int ctas = (nblk + teams - 1) / teams;
   if (ctas > sm_count) ctas = sm_count;
   const int th = teams * 64;
-  switch (variant & 3) {
+  switch (variant & 7) {
     case 1: return launch6v<1>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 2: return launch6v<2>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 3: return launch6v<3>(a, ctas, th, smem, pw_bytes, teams, sig, st);
+    case 7: return launch6v<7>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     default: return launch6v<0>(a, ctas, th, smem, pw_bytes, teams, sig, st);
   }
 }

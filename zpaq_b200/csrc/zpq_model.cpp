@@ -473,6 +473,7 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
     T.ok = ok ? 1 : 0;
   }
   build_wave_plan(M);
+  build_hash_plan(M);
   // two-warp decoder: needs the self-contained (flattened) recipes, and every ISSE fed by an ICM or ISSE
   {
     bool ok = M->fast.ok && M->wave.ok;
