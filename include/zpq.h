@@ -141,11 +141,21 @@ int zpq_compress_blocks(zpq_ctx* ctx, int nblk, const char* method,
                         int32_t* status);
 /* Batched libzpaq::decompress (libzpaq.cpp:2376-2389) over one in-memory
  * archive: finds every block (Decompresser::findBlock, libzpaq.cpp:2247),
- * decodes all of them concurrently, strips the PASS prefix, verifies stored
- * SHA-1s and writes the payloads back to back in archive order. */
+ * decodes all modelled blocks concurrently on the GPU, post-processes on the
+ * host (PASS prefix stripped; a PCOMP program -- BWT / LZ77 / E8E9 inverse
+ * transforms -- is run by the host ZPAQL machine; unmodelled level-2 blocks are
+ * unpacked on the host), verifies stored SHA-1s and writes the payloads back to
+ * back in archive order. */
 int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len,
                            uint8_t* out, uint64_t out_cap, uint64_t* out_len, int* nblocks,
                            int verify_sha1);
+/* Host-side PostProcessor (libzpaq.cpp:2183-2241) for callers that bind at the hot-path level: `model_out` is what
+ * zpq_decode_blocks returned for one block (nseg segments, lengths seg_len[]).  Its first byte is 0 (PASS: the rest is
+ * the payload) or 1 (PROG: a PCOMP program follows and every later byte is run through it).  Writes the payload of all
+ * segments back to back (out_len = total, even when it exceeds out_cap -> ZPQ_E_OUTPUT_FULL); seg_out[] (optional)
+ * receives the per-segment payload sizes.  hdr = the block header (for its ph / pm sizes).  No device is involved. */
+int zpq_postprocess_block(const uint8_t* hdr, int hlen, const uint8_t* model_out, const uint64_t* seg_len, int nseg,
+                          uint8_t* out, uint64_t out_cap, uint64_t* out_len, uint64_t* seg_out);
 /* Upper bound of a compressed block for `len` payload bytes. */
 uint64_t zpq_compress_bound(uint64_t len);
 

@@ -84,3 +84,14 @@ def test_per_block_errors_do_not_fail_the_batch(ctx):
     bad = bytearray(hdr); bad[hdr.index(bytes([0]), 7 + 2) + 1] = 0
     st, _ = ctx.encode_blocks([bytes(bad)], [b"\0" + d])[0]
     assert st in (-3, -1)
+
+
+def test_decompress_archive_every_block_type(ctx):
+    """One archive holding stored (level 2) blocks, LZ77 / BWT / E8E9 blocks with their PCOMP programs and plain
+    context-model blocks, all written by the unmodified reference: modelled blocks are decoded on the GPU, the
+    post-processing (host ZPAQL machine) and the stored blocks are handled on the host; SHA-1s are verified."""
+    post = load("postproc.json")
+    arcs = [archive_bytes(e) for e in post] + [archive_bytes(a) for a in CB_SMALL[:6] if a["how"]["dosha1"]]
+    pays = [data_of(e["data"]) for e in post] + [data_of(a["data"]) for a in CB_SMALL[:6] if a["how"]["dosha1"]]
+    out, nb = ctx.decompress_archive(b"".join(arcs), sum(map(len, pays)) + 16)
+    assert nb == len(pays) and out == b"".join(pays)

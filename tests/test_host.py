@@ -90,3 +90,30 @@ def test_kernel_plan_for_baseline_models():
         assert info[3] == 1, "HCOMP of makeConfig models must run as lane-parallel recipes"
         assert info[5] == 1, "fast kernel plan expected"
         assert 38528 + 7 * info[2] <= 232448, "level-5 tables must fit 7 blocks per SM"
+
+
+POST = load("postproc.json")
+
+
+@pytest.mark.parametrize("entry", POST, ids=["%s_k%d" % (e["method"].split(",")[0] + str(i), e["data"]["kind"]) for i, e in enumerate(POST)])
+def test_host_postprocessor_against_reference_archives(entry):
+    """zpq_postprocess_block (PASS prefix / PCOMP programs: LZ77, BWT, E8E9 inverse transforms; PostProcessor::write,
+    libzpaq.cpp:2193-2241) on archives written by the unmodified reference.  The model output comes from the CPU oracle
+    (or, for unmodelled level-2 blocks, from unpacking the stored chunks), so no GPU is involved."""
+    import base64
+    arc = base64.b64decode(entry["archive_b64"])
+    want = data_of(entry["data"])
+    blk = O.parse_blocks(arc)[0]
+    hdr = blk.header
+    coded = blk.segments[0].coded
+    if hdr[6] == 0:
+        raw = arc[arc.index(coded):]                  # 4-byte big-endian length + bytes ... zero length (libzpaq.cpp:2138-2153)
+        mo, pos = b"", 0
+        while True:
+            ln = int.from_bytes(raw[pos:pos + 4], "big"); pos += 4
+            if ln == 0:
+                break
+            mo += raw[pos:pos + ln]; pos += ln
+    else:
+        mo = O.decode(hdr, coded + b"\0\0\0\0", 4 * len(want) + 70000)
+    assert Z.postprocess_block(hdr, [mo]) == [want]

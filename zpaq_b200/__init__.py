@@ -39,7 +39,7 @@ EXPORTS = ["zpq_abi_version", "zpq_create", "zpq_destroy", "zpq_strerror", "zpq_
            "zpq_set_workspace", "zpq_set_stream", "zpq_model_bytes", "zpq_model_from_method",
            "zpq_encode_blocks", "zpq_decode_blocks", "zpq_encode_blocks_dev", "zpq_decode_blocks_dev",
            "zpq_last_timing", "zpq_launch_count", "zpq_compress_blocks", "zpq_decompress_archive",
-           "zpq_compress_bound"]
+           "zpq_compress_bound", "zpq_postprocess_block", "zpq_model_describe"]
 
 _lib = None
 
@@ -73,6 +73,7 @@ def lib():
         L.zpq_compress_blocks.argtypes = [vp, i32, C.c_char_p, vp, vp, vp, vp, i32, vp, vp, vp, vp]
         L.zpq_decompress_archive.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(i32), i32]
         L.zpq_compress_bound.argtypes = [u64]
+        L.zpq_postprocess_block.argtypes = [C.c_char_p, i32, vp, vp, i32, vp, u64, C.POINTER(u64), vp]
         L.zpq_compress_bound.restype = u64
         _lib = L
     return _lib
@@ -89,6 +90,31 @@ def model_from_method(method, data=b""):
     if rc:
         raise ZpqError(rc)
     return out.raw[:n.value]
+
+
+def postprocess_block(hdr, model_out_segments):
+    """Host PostProcessor over the model output of one block (list of per-segment bytes) -> list of payload segments."""
+    segs = [bytes(x) for x in model_out_segments]
+    flat = b"".join(segs)
+    a = C.create_string_buffer(flat, max(len(flat), 1))
+    sl = (C.c_uint64 * len(segs))(*[len(x) for x in segs])
+    so = (C.c_uint64 * len(segs))()
+    n = C.c_uint64(0)
+    cap = max(len(flat) * 4, 1 << 16)
+    while True:
+        out = C.create_string_buffer(cap)
+        rc = lib().zpq_postprocess_block(bytes(hdr), len(hdr), _addr(a), C.cast(sl, C.c_void_p), len(segs), _addr(out), cap, C.byref(n), C.cast(so, C.c_void_p))
+        if rc == -4 and n.value > cap:
+            cap = n.value
+            continue
+        if rc:
+            raise ZpqError(rc)
+        break
+    res, pos = [], 0
+    for k in range(len(segs)):
+        res.append(out.raw[pos:pos + so[k]])
+        pos += so[k]
+    return res
 
 
 def model_bytes(hdr):

@@ -572,6 +572,19 @@ int zpq_last_timing(const zpq_ctx* ctx, float ms[3]) {
 
 uint64_t zpq_launch_count(const zpq_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int zpq_postprocess_block(const uint8_t* hdr, int hlen, const uint8_t* model_out, const uint64_t* seg_len, int nseg,
+                          uint8_t* out, uint64_t out_cap, uint64_t* out_len, uint64_t* seg_out) {
+  if (!hdr || hlen < 7 || !model_out || !seg_len || nseg < 1 || !out_len) return ZPQ_E_ARG;
+  std::vector<uint8_t> payload; std::vector<uint64_t> segs; std::string e;
+  const int rc = postprocess_block(hdr[4], hdr[5], model_out, seg_len, nseg, &payload, &segs, &e);
+  if (rc != ZPQ_OK) return rc;
+  *out_len = payload.size();
+  if (seg_out) for (int i = 0; i < nseg; ++i) seg_out[i] = segs[i];
+  if (payload.size() > out_cap || (!out && !payload.empty())) return ZPQ_E_OUTPUT_FULL;
+  if (!payload.empty()) memcpy(out, payload.data(), payload.size());
+  return ZPQ_OK;
+}
+
 uint64_t zpq_compress_bound(uint64_t len) { return len + len / 8 + 1024; }
 
 // Batched libzpaq::compressBlock (libzpaq.cpp:7543-7731), context-model family only.
@@ -690,7 +703,13 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
 
   std::vector<std::vector<uint8_t>> tmp;
   std::vector<uint64_t> pos(nb, 0);
-  bool direct = all_hinted;
+  // unmodelled blocks (n = 0, level 2) have nothing to decode: their "model output" is the stored chunks back to back
+  // (4-byte big-endian length + bytes, zero length ends the segment; Decoder::decompress libzpaq.cpp:2138-2153).  They
+  // are unpacked here on the host and only meet the other blocks again at the post-processing step.
+  std::vector<char> stored(nb, 0);
+  bool any_stored = false;
+  for (size_t i = 0; i < nb; ++i) if (jobs[i].hlen > 6 && jobs[i].hdr[6] == 0) { stored[i] = 1; any_stored = true; }
+  bool direct = all_hinted && !any_stored;
   if (direct) {
     uint64_t p = 0;
     for (size_t i = 0; i < nb; ++i) { pos[i] = p; p += (uint64_t)hint[i]; }
@@ -703,13 +722,38 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
     rc = run_batch(ctx, jobs, true, false);
     if (rc != ZPQ_OK) return rc;
     for (size_t i = 0; i < nb && direct; ++i)
-      if (jobs[i].status == ZPQ_E_OUTPUT_FULL || (jobs[i].status == ZPQ_OK && jobs[i].out_len != (uint64_t)hint[i] + 1))
-        direct = false;     // a comment lied about the size: redo through staging
+      if (jobs[i].status == ZPQ_E_OUTPUT_FULL || (jobs[i].status == ZPQ_OK && (jobs[i].out_len != (uint64_t)hint[i] + 1 || jobs[i].first_byte != 0)))
+        direct = false;     // a comment lied about the size, or the block carries a PCOMP program: redo through staging
   }
+  // blocks whose model output starts with 1 (PROG) are post-processed on the host after staging (zpq_hcomp.cpp postprocess_block)
+  std::vector<std::vector<uint8_t>> post(nb);
+  std::vector<std::vector<uint64_t>> post_seg(nb);
+  std::vector<char> is_prog(nb, 0);
+  std::vector<int> post_rc(nb, ZPQ_OK);
   if (!direct) {
     tmp.resize(nb);
-    std::vector<size_t> pending(nb);
-    for (size_t i = 0; i < nb; ++i) pending[i] = i;
+    std::vector<size_t> pending;
+    for (size_t i = 0; i < nb; ++i) {
+      if (!stored[i]) { pending.push_back(i); continue; }
+      IJob& J = jobs[i];
+      J.status = ZPQ_OK; J.seg_out.assign(bv[i].segs.size(), 0);
+      for (size_t sg = 0; sg < bv[i].segs.size() && J.status == ZPQ_OK; ++sg) {
+        const uint8_t* a = arc + bv[i].segs[sg].coded_off; const uint64_t n = bv[i].segs[sg].coded_len;
+        uint64_t e = 0;
+        for (;;) {
+          if (e + 4 > n) { J.status = ZPQ_E_EOF; break; }
+          const uint64_t len = (uint64_t)a[e] << 24 | (uint64_t)a[e + 1] << 16 | (uint64_t)a[e + 2] << 8 | a[e + 3];
+          e += 4;
+          if (len == 0) break;
+          if (e + len > n) { J.status = ZPQ_E_EOF; break; }
+          tmp[i].insert(tmp[i].end(), a + e, a + e + len);
+          J.seg_out[sg] += len;
+          e += len;
+        }
+      }
+      J.out_len = tmp[i].size();
+      J.first_byte = tmp[i].empty() ? -1 : tmp[i][0];
+    }
     std::vector<uint64_t> cap(nb);
     for (size_t i = 0; i < nb; ++i) cap[i] = hint[i] >= 0 ? (uint64_t)hint[i] + 1 : (uint64_t)4 << 20;
     while (!pending.empty()) {
@@ -734,12 +778,30 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
       }
       pending.swap(again);
     }
+    {
+      std::vector<size_t> progs;
+      for (size_t i = 0; i < nb; ++i)
+        if (jobs[i].status == ZPQ_OK && jobs[i].out_len >= 1 && tmp[i][0] == 1) { is_prog[i] = 1; progs.push_back(i); }
+      const unsigned nt = (unsigned)std::min<size_t>(progs.size(), std::max(1u, std::min(std::thread::hardware_concurrency(), 64u)));
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() {
+          for (size_t k = t; k < progs.size(); k += nt) {
+            const size_t i = progs[k];
+            std::string pe;
+            post_rc[i] = postprocess_block(jobs[i].hdr[4], jobs[i].hdr[5], tmp[i].data(), jobs[i].seg_out.data(), (int)jobs[i].seg_out.size(),
+                                           &post[i], &post_seg[i], &pe);
+          }
+        });
+      for (auto& t : th) t.join();
+    }
     uint64_t p = 0;
     for (size_t i = 0; i < nb; ++i) {
       pos[i] = p;
-      if (jobs[i].status != ZPQ_OK || jobs[i].out_len < 1) continue;
-      const uint64_t n = jobs[i].out_len - 1;
-      if (p + n <= out_cap && out) memcpy(out + p, tmp[i].data() + 1, n);
+      if (jobs[i].status != ZPQ_OK || jobs[i].out_len < 1 || post_rc[i] != ZPQ_OK) continue;
+      const uint64_t n = is_prog[i] ? post[i].size() : jobs[i].out_len - 1;
+      const uint8_t* src = is_prog[i] ? post[i].data() : tmp[i].data() + 1;
+      if (p + n <= out_cap && out) { if (n) memcpy(out + p, src, n); }
       else note(ZPQ_E_OUTPUT_FULL);
       p += n;
     }
@@ -756,11 +818,13 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
           const IJob& J = jobs[i];
           if (J.status != ZPQ_OK) { st[i] = J.status; continue; }
           if (J.out_len < 1) { st[i] = ZPQ_E_CORRUPT; continue; }
-          if (J.first_byte != 0) { st[i] = ZPQ_E_UNSUPPORTED; continue; }   // PROG: PCOMP post-processing, outside this path
-          if (!verify_sha1 || pos[i] + J.out_len - 1 > out_cap || !out) continue;
+          if (post_rc[i] != ZPQ_OK) { st[i] = post_rc[i]; continue; }
+          if (J.first_byte != 0 && !is_prog[i]) { st[i] = ZPQ_E_CORRUPT; continue; }   // "unknown post processing type"
+          const uint64_t total_i = is_prog[i] ? post[i].size() : J.out_len - 1;
+          if (!verify_sha1 || pos[i] + total_i > out_cap || !out) continue;
           uint64_t at = pos[i];
           for (size_t s = 0; s < J.seg_out.size(); ++s) {
-            const uint64_t n = J.seg_out[s] - (s == 0 ? 1 : 0);
+            const uint64_t n = is_prog[i] ? post_seg[i][s] : J.seg_out[s] - (s == 0 ? 1 : 0);
             if (bv[i].segs[s].has_sha1) {
               uint8_t d[20];
               sha1_of(out + at, n, d);
@@ -775,9 +839,8 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
   uint64_t total = 0;
   for (size_t i = 0; i < nb; ++i) {
     note(st[i]);
-    if (st[i] == ZPQ_OK || st[i] == ZPQ_E_CHECKSUM) total = pos[i] + jobs[i].out_len - 1;
+    if (st[i] == ZPQ_OK || st[i] == ZPQ_E_CHECKSUM) total = pos[i] + (is_prog[i] ? post[i].size() : jobs[i].out_len - 1);
   }
-  if (first_bad == ZPQ_E_UNSUPPORTED) ctx->err = "PCOMP post-processing is outside the context-mixing path";
   *out_len = total;
   return first_bad;
 }

@@ -32,13 +32,15 @@ struct HostVm {
   std::vector<uint8_t> m; std::vector<uint32_t> h; uint32_t r[256];
   uint32_t a = 0, b = 0, c = 0, d = 0; int f = 0;
   const uint8_t* code; int len;
+  std::vector<uint8_t>* out = nullptr;      // OUT (opcode 57) appends here; PCOMP only
+  long long max_steps = 1 << 20;            // per run(); the self-checks keep it small, post-processing raises it
   HostVm(int hh, int hm, const uint8_t* prog, int n) : m((size_t)1 << hm, 0), h((size_t)1 << hh, 0), code(prog), len(n) { memset(r, 0, sizeof(r)); }
   uint8_t fetch(int pc) const { return (pc >= 0 && pc < len) ? code[pc] : 0; }
   bool run(uint32_t input) {
     const uint32_t mm = (uint32_t)m.size() - 1, hm = (uint32_t)h.size() - 1;
     a = input;
     int pc = 0;
-    for (int guard = 0; guard < (1 << 20); ++guard) {
+    for (long long guard = 0; guard < max_steps; ++guard) {
       const int op = fetch(pc++);
       if (op == 56) return true;
       if (op < 56) {
@@ -65,7 +67,7 @@ struct HostVm {
         continue;
       }
       if (op < 64) {
-        if (op == 57) continue;
+        if (op == 57) { if (out) out->push_back((uint8_t)a); continue; }
         if (op == 59) { a = (a + m[b & mm] + 512) * 773; continue; }
         if (op == 60) { h[d & hm] = (h[d & hm] + a + 512) * 773; continue; }
         if (op == 63) { const int n = fetch(pc); pc += ((n + 128) & 255) - 127; continue; }
@@ -546,6 +548,59 @@ void build_hash_plan(ZModel* M) {
       if (fe[l].step(W.flat[l], W.flat_len[l], byte, M->pipe.dist_byte[l]) != h[l]) return;
   }
   P.ok = 1;
+}
+
+
+// ---------------------------------------------------------------------------
+// Post-processing of one block's model output (PostProcessor::write, libzpaq.cpp:2193-2241), host side: the first
+// byte through the model is 0 (PASS: the rest is the payload) or 1 (PROG: two length bytes and a PCOMP program follow;
+// every later byte, and 0xffffffff at the end of each segment, is run through that program, whose OUT instructions
+// produce the payload).  This is not part of the GPU hot path: it runs on the host after the block is decoded.
+int postprocess_block(int ph, int pm, const uint8_t* model_out, const uint64_t* seg_len, int nseg,
+                      std::vector<uint8_t>* payload, std::vector<uint64_t>* seg_payload, std::string* err) {
+  payload->clear(); seg_payload->assign((size_t)std::max(nseg, 0), 0);
+  int state = 0;                 // 0 first byte, 1 PASS, 2/3 length bytes, 4 program bytes, 5 running
+  size_t want = 0;
+  std::vector<uint8_t> prog;
+  HostVm* vm = nullptr;
+  int rc = ZPQ_OK;
+  const uint8_t* p = model_out;
+  for (int sg = 0; sg < nseg && rc == ZPQ_OK; ++sg) {
+    const size_t before = payload->size();
+    for (uint64_t i = 0; i < seg_len[sg] && rc == ZPQ_OK; ++i) {
+      const uint32_t c = *p++;
+      switch (state) {
+        case 0:
+          if (c > 1) { if (err) *err = "unknown post processing type"; rc = ZPQ_E_CORRUPT; }
+          else state = c == 0 ? 1 : 2;
+          break;
+        case 1: payload->push_back((uint8_t)c); break;
+        case 2: want = c; state = 3; break;
+        case 3:
+          want += (size_t)c * 256;
+          if (want < 1) { if (err) *err = "Empty PCOMP"; rc = ZPQ_E_CORRUPT; }
+          prog.reserve(want); state = 4;
+          break;
+        case 4:
+          prog.push_back((uint8_t)c);
+          if (prog.size() == want) {
+            vm = new HostVm(ph, pm, prog.data(), (int)prog.size());     // ZPAQL::initp: H = 2^ph words, M = 2^pm bytes
+            vm->out = payload; vm->max_steps = (long long)1 << 40;
+            state = 5;
+          }
+          break;
+        default:
+          if (!vm->run(c)) { if (err) *err = "ZPAQL execution error"; rc = ZPQ_E_VM; }
+      }
+    }
+    if (rc == ZPQ_OK) {
+      if (state == 5) { if (!vm->run(0xffffffffu)) { if (err) *err = "ZPAQL execution error"; rc = ZPQ_E_VM; } }
+      else if (state != 1) { if (err) *err = "Unexpected EOS"; rc = ZPQ_E_CORRUPT; }
+    }
+    (*seg_payload)[sg] = payload->size() - before;
+  }
+  delete vm;
+  return rc;
 }
 
 }  // namespace zpq

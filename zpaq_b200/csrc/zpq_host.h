@@ -19,7 +19,10 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
 // zpq_hcomp.cpp : HCOMP bytecode -> lane-parallel recipes (self-checked)
 void build_recipes(ZModel* M, const uint8_t* prog, int prog_len);
 void build_wave_plan(ZModel* M);   // after the pipe plan: flattened recipes for the wavefront encoder
-void build_hash_plan(ZModel* M);   // after the wave plan: slot-scheduled hashes for the two-warp decoder
+void build_hash_plan(ZModel* M);
+// PostProcessor (libzpaq.cpp:2183-2241) over a decoded block: PASS prefix stripped or PCOMP program run, per segment
+int postprocess_block(int ph, int pm, const uint8_t* model_out, const uint64_t* seg_len, int nseg,
+                      std::vector<uint8_t>* payload, std::vector<uint64_t>* seg_payload, std::string* err);   // after the wave plan: slot-scheduled hashes for the two-warp decoder
 
 // zpq_method.cpp : method string (+ payload statistics) -> block header bytes
 int header_from_method(const char* method, const uint8_t* data, uint64_t n,
