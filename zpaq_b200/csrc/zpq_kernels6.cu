@@ -269,7 +269,12 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       }
       int mixw0 = 0, mixw1 = 0, mixw2 = 0, mixx0 = 0, mixx1 = 0, mixx2 = 0; u32 sserow0 = 0, sserow1 = 0;
       u32 cxt = 0, v0 = 0; int xj = 0, xk = 0;
-      u32 ma = 0, mb = 0, mpos = 0, mbit = 0, mpred = 0, mc = 0;
+      u32 ma = 0, mb = 0, mpos = 0, mbit = 0, mpred = 0, mc = 0, mdt = 0;
+      // MIX: ((h + (c8 & mask)) & (size-1)) * m   MIX2: (h + (c8 & mask)) & (size-1)   SSE: ((h + c8) * 32) & (32*size-1)
+      const bool ctx_on = type == ZT_MIX || type == ZT_MIX2 || type == ZT_SSE;
+      const u32 ctx_m1 = type == ZT_SSE ? 0xffffffffu : a5;
+      const u32 ctx_m2 = type == ZT_SSE ? cm_mask >> 5 : cm_mask;
+      const u32 ctx_mul = type == ZT_MIX ? a3 : (type == ZT_SSE ? 32u : 1u);
       // candidate rows of the next bit (V bit 1): valid when every MIX has a full c8 mask and >= 256 rows and
       // every SSE has >= 256 rows, so that the two candidate rows differ from the row trained in this bit
       int mc00 = 0, mc01 = 0, mc10 = 0, mc11 = 0, mc20 = 0, mc21 = 0; u32 sc00 = 0, sc01 = 0, sc10 = 0, sc11 = 0;
@@ -319,22 +324,19 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
               if (ma == 0) p = 0;
               else {
                 mc = (mpred >> (7 - mbit)) & 1u;
-                p = t_stretch(S, (u32)((int)(2048u / ma) * (1 - 2 * (int)mc)) & 32767u);
+                p = t_stretch(S, (u32)((int)mdt * (1 - 2 * (int)mc)) & 32767u);      // mdt = dt2k[ma] = 2048 / ma
               }
             }
-            else if (type == ZT_MIX2) {
-              cxt = (h + (u32)(c8 & (int)a5)) & cm_mask;
-              v0 = reinterpret_cast<const u16*>(gtab)[cxt];
-            }
+            // row / entry of the components indexed by h + c8: one formula with per-lane constants (set per block).
             // cxn0 / cxn1 = the row of the NEXT bit when this bit decodes to 0 / 1
             u32 cxn0 = 0, cxn1 = 0;
-            if (type == ZT_MIX) {
-              cxt = ((h + (u32)(c8 & (int)a5)) & cm_mask) * a3;
-              if (V & 2) { cxn0 = ((h + (u32)((c8 * 2) & (int)a5)) & cm_mask) * a3; cxn1 = ((h + (u32)((c8 * 2 + 1) & (int)a5)) & cm_mask) * a3; }
-            }
-            else if (type == ZT_SSE) {
-              cxt = ((h + (u32)c8) * 32u) & cm_mask;
-              if (V & 2) { cxn0 = ((h + (u32)(c8 * 2)) * 32u) & cm_mask; cxn1 = ((h + (u32)(c8 * 2 + 1)) * 32u) & cm_mask; }
+            if (ctx_on) {
+              cxt = ((h + ((u32)c8 & ctx_m1)) & ctx_m2) * ctx_mul;
+              if (V & 2) {
+                cxn0 = ((h + ((u32)(c8 * 2) & ctx_m1)) & ctx_m2) * ctx_mul;
+                cxn1 = ((h + ((u32)(c8 * 2 + 1) & ctx_m1)) & ctx_m2) * ctx_mul;
+              }
+              if (type == ZT_MIX2) v0 = reinterpret_cast<const u16*>(gtab)[cxt];
             }
             const bool use_cand = (V & 2) && candv;
             candv = (V & 2) && cand_ok && c8 < 128;
@@ -458,6 +460,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
                 else ma += (ma < 255);
                 *idx = mpos;
                 mpred = ht[(mpos - mb) & ht_mask];
+                mdt = ma ? 2048u / ma : 0u;                 // once per byte instead of once per bit
               }
             }
 #pragma unroll
