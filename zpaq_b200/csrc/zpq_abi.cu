@@ -66,7 +66,7 @@ struct zpq_ctx {
   uint64_t launches = 0;
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
-  int wave_variant = 1;        // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches
+  int wave_variant = 5;        // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads
   int dec_variant = 7;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7) slot-scheduled hashes
   bool wave_prof = false;      // ZPQ_WAVE_PROF=1: per-role warp cycles of the wavefront encoder to stderr
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
@@ -313,6 +313,13 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           Wv.group_first = d_gfirst; Wv.group_count = d_gcount; Wv.blk_group = d_bgroup; Wv.blk_lane = d_blane;
           Wv.chunk_bytes = CB; Wv.ncs = ncs; Wv.ngroups = ngroups; Wv.gsize = GS;
           Wv.prof = nullptr;
+          // ZPQ_WAVE_VARIANT bit 2: mixers as component threads, when every MIX of every model in the launch qualifies
+          Wv.mix_threads = (ctx->wave_variant & 4) ? 1 : 0;
+          for (int k = first; k < first + cnt && Wv.mix_threads; ++k) {
+            const ZModel& Mk = models[jobs[wave[k]].model];
+            for (uint32_t ci = 0; ci < Mk.n; ++ci)
+              if (Mk.comp[ci].type == ZT_MIX && !((Mk.comp[ci].a5 & 255u) == 255u && Mk.comp[ci].cm_mask >= 255u)) Wv.mix_threads = 0;
+          }
           if (ctx->wave_prof) { CK(cudaMemsetAsync(d_prof, 0, 64 * 8, st), "memset prof"); Wv.prof = d_prof; }
           const int nwaves = (int)((maxN + CB - 1) / CB) + (int)dmaxc + 1;
           for (int w = 0; w < std::max(nwaves, (int)dmaxc + 1); ++w) {
@@ -474,7 +481,7 @@ int zpq_create(int device, zpq_ctx** out) {
   ctx->device = device;
   if (const char* gs = getenv("ZPQ_GROUP")) { const int v = atoi(gs); if (v >= 1 && v <= 32) ctx->wave_group = v; }
   if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
-  if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 3) ctx->wave_variant = v; }
+  if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 7) ctx->wave_variant = v; }
   if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if ((v >= 0 && v <= 3) || v == 7) ctx->dec_variant = v; }
   if (const char* wp = getenv("ZPQ_WAVE_PROF")) ctx->wave_prof = atoi(wp) != 0;
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }

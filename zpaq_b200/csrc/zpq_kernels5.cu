@@ -15,7 +15,8 @@
 //   * predictions travel through HBM streams (one 16-byte vector of eight int16 per component per
 //     byte, laid out [group][component][chunk slot][byte][lane] so that a warp reads and writes 512
 //     contiguous bytes); a stream written in wave w is read in waves w+1 .. w+15;
-//   * MIX components get a whole warp per block (lane = input, coalesced weight row, redux.sync);
+//   * MIX components with a full c8 mask are component threads too (eight independent weight rows per byte, see
+//     the ZT_MIX branch); other mixers get a whole warp per block (lane = input, coalesced weight row, redux.sync);
 //   * kernel boundaries are the only synchronisation.
 //
 // Context hashes come from the flattened recipes of zpq_hcomp.cpp (build_wave_plan): each thread
@@ -123,7 +124,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
     if (c >= n) return -1;
     const ZComp cd = ZM->comp[c];
     const u32 type = cd.type;
-    if (type == ZT_MIX) return -1;                                  // mixers have their own warps below
+    if (type == ZT_MIX && !W.mix_threads) return -1;                // mixers have their own warps below
     const int ch = W.wave - (int)ZM->pipe.depth[c];
     if (ch < 0) return -1;
     const int b0 = ch * CB;
@@ -146,6 +147,63 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
     u32 dist_last = cs[7];
     u32 ma = cs[8], mb = cs[9], mpos = cs[10], mpred = cs[11], mc = 0;
     u32 h_next = h;
+    if (type == ZT_MIX) {
+      // ---------------- MIX as a component thread (W.mix_threads) ----------------
+      // With a full c8 mask and >= 256 weight sets the eight bits of a byte use eight DIFFERENT weight rows, and a row
+      // trained in this byte is next read in a later byte: the eight dot products of a byte are independent.  One thread
+      // then codes a whole block's mixer: per byte it walks the m inputs twice (sums, then training), eight rows at a
+      // time, instead of a warp spending ~150 instructions per bit on one block.  Same operations on the same weights
+      // in an order that differs only between rows that do not interact -> same bytes.
+      const int m = (int)a3, j0 = (int)a2, rate = (int)a4;
+      int* const tab = reinterpret_cast<int*>(gtab);
+      for (int pos = b0; pos < b1; ++pos) {
+        const u32 cur = in[pos];
+        const int i = pos - b0;
+        u32 bb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bb[k] = ((h + (((0x100u | cur) >> (8 - k)) & a5)) & cm_mask) * (u32)m;
+        int sum[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum[k] = 0;
+        for (int j = 0; j < m; ++j) {
+          const uint4 v = pb[PBIDX(j0 + j, slot, i)];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) sum[k] += (tab[bb[k] + (u32)j] >> 8) * vget(v, k);
+        }
+        int err[8];
+        uint4 vout = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int pk = clamp2k(sum[k] >> 8);
+          const int y = (int)((cur >> (7 - k)) & 1u);
+          err[k] = ((y * 32767 - t_squash(S, pk)) * rate) >> 4;
+          vset(vout, k, pk);
+        }
+        for (int j = 0; j < m; ++j) {
+          const uint4 v = pb[PBIDX(j0 + j, slot, i)];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            int* const wp = tab + bb[k] + (u32)j;
+            *wp = clamp512k(*wp + ((err[k] * vget(v, k) + (1 << 12)) >> 13));
+          }
+        }
+        pb[PBIDX(c, slot, i)] = vout;
+        const u64 hs = (hist << 8) | (u64)cur;
+        h = flat_eval(fops, flen, st, cur, hs, pos, in, 0u);
+        hist = hs;
+        if (pos + 1 < b1) {                      // the next byte's eight rows are known now: pull them towards L2
+          const u32 nxt = in[pos + 1];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int* const r = tab + ((h + (((0x100u | nxt) >> (8 - k)) & a5)) & cm_mask) * (u32)m;
+            prefetch_l2(r); prefetch_l2(r + m - 1);
+          }
+        }
+      }
+      cs[0] = h; cs[1] = st[0]; cs[2] = st[1]; cs[3] = st[2]; cs[4] = st[3];
+      cs[5] = (u32)hist; cs[6] = (u32)(hist >> 32);
+      return 11;
+    }
     int p = (type == ZT_CONS) ? ((int)a1 - 128) * 4 : 0;
     uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
     uint4 pf0 = row, pf1 = row, pf2 = row; u32 pf_h0 = 0; bool pf_valid = false;
@@ -383,7 +441,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
   // =========================================================================================
   // MIX warps: warp = (block, mixer); lane l = input l
   // =========================================================================================
-  if (ROLE != 1) {
+  if (ROLE != 1 && !W.mix_threads) {
     const int idx = gw - nA;
     const int bi = idx / ZPQ_FAST_MIX, q = idx - bi * ZPQ_FAST_MIX;
     if (bi >= A.nblk) return -1;
@@ -548,7 +606,8 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
 // ---------------------------------------------------------------------------
 extern "C" cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant) {
   // variant bit 0: byte-ahead weight rows in the MIX warps; bit 1: component threads and MIX warps as two launches
-  const int wa = w->ngroups * w->ncs, wm = w->A.nblk * ZPQ_FAST_MIX;
+  // (w->mix_threads: the mixers are component threads, there are no MIX warps to launch)
+  const int wa = w->ngroups * w->ncs, wm = w->mix_threads ? 0 : w->A.nblk * ZPQ_FAST_MIX;
   if (wa + wm <= 0) return cudaSuccess;
   const bool pf = (variant & 1) != 0;
   if (variant & 2) {
