@@ -130,6 +130,9 @@ struct ZWave {
   uint32_t ok;
   uint32_t dcoder;                         // depth of the coder stage = depth[n-1] + 1
   uint32_t flat_len[ZPQ_MAX_LANES];
+  uint8_t fold_n[ZPQ_MAX_LANES];           // n+1 when the recipe is exactly "hash of the last n bytes" (n = 0..8: zero start, then
+                                           // (acc + byte[k] + 512) * 773 for k = 0..n-1): evaluated from the history register
+                                           // without interpreting the op list; 0 = general recipe
   alignas(16) uint32_t flat[ZPQ_MAX_LANES][ZPQ_FLAT_MAX];   // rows of 160 bytes, fetched 16 bytes at a time
 };
 

@@ -424,6 +424,14 @@ void build_wave_plan(ZModel* M) {
     for (int l = 0; l < n; ++l)
       if (fe[l].step(W.flat[l], W.flat_len[l], byte, M->pipe.dist_byte[l]) != rc.h[l]) return;
   }
+  // shape of the common recipes: order-n hash of the last n bytes (the ICM / ISSE chain of makeConfig), or constant 0
+  for (int l = 0; l < n; ++l) {
+    const uint32_t len = W.flat_len[l];
+    bool fold = len >= 1 && len <= 9 && W.flat[l][0] == ((uint32_t)ZR_SEG | (uint32_t)ZB_ZERO << 4);
+    for (uint32_t t = 1; t < len && fold; ++t)
+      fold = W.flat[l][t] == ZR_WORD_OF(ZR_FOLD, ZS_BYTE, 255, t - 1);
+    W.fold_n[l] = fold ? (uint8_t)len : 0;        // len = n + 1 (the segment op, then n folds)
+  }
   W.dcoder = M->pipe.depth[n - 1] + 1;
   if (W.dcoder > 15) return;
   W.ok = 1;

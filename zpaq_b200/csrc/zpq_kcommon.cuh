@@ -153,6 +153,19 @@ __device__ __forceinline__ u32 flat_eval(const u32* __restrict__ ops, u32 len, u
 }
 
 
+// Recipe of a wavefront-encoder thread: the order-n byte hash (ZWave.fold_n = n + 1) straight from the history register,
+// any other recipe through the flat interpreter.  hs = the last eight bytes, newest in the low byte.
+__device__ __forceinline__ u32 wave_hash(u32 fold_n1, const u32* __restrict__ ops, u32 len, u32 st[ZPQ_FLAT_SEGS], u32 cur, u64 hs,
+                                         int bpos, const u8* in, u32 dist_last) {
+  if (fold_n1) {
+    u32 acc = 0;
+    for (u32 k = 0; k + 1 < fold_n1; ++k) acc = (acc + ((u32)(hs >> (8u * k)) & 255u) + 512u) * 773u;
+    st[0] = acc;
+    return acc;
+  }
+  return flat_eval(ops, len, st, cur, hs, bpos, in, dist_last);
+}
+
 // Slot-scheduled hashes (ZHashPlan, zpq_dev.h): the recipes of all lanes as ONE sequence of slots with a warp-uniform op
 // kind, so the loop below has no per-lane control flow apart from the rare byte sources older than 8 bytes and the
 // position-modulo source.  `mine_mask` = lanes of this warp that own a component (slots without any of them are skipped),

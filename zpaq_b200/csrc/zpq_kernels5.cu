@@ -138,6 +138,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
     u8* const ht = arena + (u64)cd.ht_off16 * 16;
     const u32* const fops = ZM->wave.flat[c];
     const u32 flen = ZM->wave.flat_len[c];
+    const u32 fold1 = ZM->wave.fold_n[c];
     const u32 dist_byte = ZM->pipe.dist_byte[c];
     const bool is_hash = (type == ZT_ICM || type == ZT_ISSE);
 
@@ -189,7 +190,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
         }
         pb[PBIDX(c, slot, i)] = vout;
         const u64 hs = (hist << 8) | (u64)cur;
-        h = flat_eval(fops, flen, st, cur, hs, pos, in, 0u);
+        h = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, 0u);
         hist = hs;
         if (pos + 1 < b1) {                      // the next byte's eight rows are known now: pull them towards L2
           const u32 nxt = in[pos + 1];
@@ -257,7 +258,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
           if (bit == 4) {
             const u64 hs = (hist << 8) | (u64)cur;
             if (cur == dist_byte) dist_last = (u32)(-(pos + 1));
-            h_next = flat_eval(fops, flen, st, cur, hs, pos, in, dist_last);
+            h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
             hist = hs;
           }
           if (is_hash) {
@@ -470,6 +471,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
     const u32 a5 = cd.a5, cmm = cd.cm_mask;
     const u32* const fops = ZM->wave.flat[cq];
     const u32 flen = ZM->wave.flat_len[cq];
+    const u32 fold1 = ZM->wave.fold_n[cq];
 
     u32 h = cs[0];
     u32 st[ZPQ_FLAT_SEGS] = {cs[1], cs[2], cs[3], cs[4]};
@@ -505,7 +507,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
         }
         // the next byte's hash needs only input data: evaluate it now and pull the next byte's rows towards L2
         const u64 hs = (hist << 8) | (u64)cur;
-        h_next = flat_eval(fops, flen, st, cur, hs, pos, in, 0u);
+        h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, 0u);
         hist = hs;
         if (more && lane < 16) {
           const int* const r = tab + ((h_next + (((0x100u | cur_n) >> (8 - kk)) & a5)) & cmm) * (u32)m;
@@ -561,7 +563,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
         for (int bit = 0; bit < 8; ++bit) {
           if (bit == 4) {
             const u64 hs = (hist << 8) | (u64)cur;
-            h_next = flat_eval(fops, flen, st, cur, hs, pos, in, 0u);
+            h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, 0u);
             hist = hs;
             if (more) {
               latem = 0u;
@@ -599,7 +601,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
       for (int bit = 0; bit < 8; ++bit) {
         if (bit == 4) {
           const u64 hs = (hist << 8) | (u64)cur;
-          h_next = flat_eval(fops, flen, st, cur, hs, pos, in, 0u);
+          h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, 0u);
           hist = hs;
         }
         const u32 c8 = (0x100u | cur) >> (8 - bit);
