@@ -234,15 +234,17 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
       }
       uint4 vout = make_uint4(0, 0, 0, 0);
 
+      // c8 / hmap4 as Predictor::update maintains them (libzpaq.cpp:2054-2066), carried from bit to bit: the bit
+      // index is a run-time value in this loop, so the closed forms would cost variable shifts and selects every bit
+      u32 c8 = 1u, hmap4 = 1u, curs = cur << 24;
 #pragma unroll 1
       for (int bit = 0; bit < 8; ++bit) {
-        const u32 c8 = (0x100u | cur) >> (8 - bit);
-        const u32 hmap4 = bit < 4 ? c8 : ((((0x10u | (cur >> 4)) << 4)) | ((0x10u | (cur & 15u)) >> (8 - bit)));
-        const int y = (int)((cur >> (7 - bit)) & 1u);
+        const int y = (int)(curs >> 31);
         const int hslot = (int)(hmap4 & 15u);
         // context of the NEXT bit (bit 7: first bit of the next byte, c8 = hmap4 = 1)
-        const u32 c8n = bit < 7 ? ((0x100u | cur) >> (7 - bit)) : 1u;
-        const u32 hmap4n = bit < 3 ? c8n : (bit < 7 ? ((((0x10u | (cur >> 4)) << 4)) | ((0x10u | (cur & 15u)) >> (7 - bit))) : 1u);
+        const u32 c8n = bit < 7 ? c8 * 2u + (u32)y : 1u;
+        const u32 hmap4n = bit == 7 ? 1u : (bit == 3 ? ((hmap4 & 0xfu) << 5 | (u32)y << 4 | 1u)
+                                                     : ((hmap4 & 0x1f0u) | (((hmap4 & 0xfu) * 2u + (u32)y) & 0xfu)));
 
         if ((bit & 3) == 0) {
           // tables indexed per bit: pull the lines of the NEXT nibble into L2 now (addresses are input data)
@@ -429,6 +431,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
           default: break;
         }
         vset(vout, bit, p);
+        c8 = c8n; hmap4 = hmap4n; curs <<= 1;
       }
       pb[PBIDX(c, slot, i)] = vout;
       h = h_next;
