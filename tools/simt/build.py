@@ -7,7 +7,7 @@ The translation is textual and touches only what g++ cannot parse:
   kernel<<<grid, block, smem, stream>>>(args);    ->  simt_launch(dim3(grid), dim3(block), smem, [&]() { kernel(args); });
   extern __shared__ ... unsigned char smem[];     ->  unsigned char* smem = simt_dyn_smem();
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory")   ->  simt_named_barrier(id, count)
-  asm volatile("prefetch.global.L2 [%0];" :: "l"(p))                   ->  (void)(p)
+  asm volatile("prefetch.global.L1|L2 [%0];" :: "l"(p))                ->  (void)(p)
   while (cond) { }      (spin on a volatile shared word)               ->  while (cond) { simt_spin(); }
 """
 import os
@@ -52,7 +52,7 @@ def translate(text, name):
     text, n_launch = LAUNCH.subn(launch, text)
     text, n_smem = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];", r"unsigned char* \1 = simt_dyn_smem();", text)
     text, n_bar = re.subn(r'asm volatile\("bar\.sync %0, %1;"\s*::\s*"r"\((.*?)\),\s*"r"\((\d+)\)\s*:\s*"memory"\)', r"simt_named_barrier(\1, \2)", text)
-    text, n_pf = re.subn(r'asm volatile\("prefetch\.global\.L2 \[%0\];"\s*::\s*"l"\((\w+)\)\)', r"(void)(\1)", text)
+    text, n_pf = re.subn(r'asm volatile\("prefetch\.global\.L[12] \[%0\];"\s*::\s*"l"\((\w+)\)\)', r"(void)(\1)", text)
     text, n_spin = re.subn(r"(while \(.*\)) \{ \}", r"\1 { simt_spin(); }", text)
     text = text.replace("__noinline__", "__attribute__((noinline))")
     if "asm" in re.sub(r"//.*", "", text):

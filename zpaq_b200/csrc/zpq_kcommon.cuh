@@ -45,6 +45,7 @@ __device__ __forceinline__ int t_squash(const Tabs& S, int x) {
   return i < 0 ? 0 : (i > 1343 ? 32767 : v);
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int clamp2k(int x) { return min(max(x, -2048), 2047); }
 __device__ __forceinline__ int clamp512k(int x) { return min(max(x, -(1 << 19)), (1 << 19) - 1); }
 

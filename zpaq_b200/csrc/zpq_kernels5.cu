@@ -215,22 +215,23 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
     u32 nx_key = 0xffffffffu, nx_a = 0, nx_b = 0, up_a = 0, up_b = 0; bool nx_ok = false, nx_same = false;
     u32 nx_key1 = 0xffffffffu;   // SSE: index of the second bucket (first is nx_key)
 
-    // inputs of byte pos+1 are requested while byte pos is coded
     const u32 in_j = (type == ZT_AVG) ? a1 : a2, in_k = (type == ZT_AVG) ? a2 : a3;
     const bool has_j = (type == ZT_ISSE || type == ZT_SSE || type == ZT_MIX2 || type == ZT_AVG);
     const bool has_k = (type == ZT_MIX2 || type == ZT_AVG);
+    // The input vectors of byte pos+1 are pulled into L1 while byte pos is coded and loaded at the top of their own byte.
+    // (Holding them in registers instead costs eight registers across the whole bit loop; at the 128-register budget of
+    // 4 CTAs per SM the compiler spilled them right behind their loads, i.e. waited for the stream read every byte.)
     u32 cur_n = in[b0];
-    uint4 vj_n = make_uint4(0, 0, 0, 0), vk_n = vj_n;
-    if (has_j) vj_n = pb[PBIDX(in_j, slot, 0)];
-    if (has_k) vk_n = pb[PBIDX(in_k, slot, 0)];
     for (int pos = b0; pos < b1; ++pos) {
       const u32 cur = cur_n;
       const int i = pos - b0;
-      const uint4 vin_j = vj_n, vin_k = vk_n;
+      uint4 vin_j = make_uint4(0, 0, 0, 0), vin_k = vin_j;
+      if (has_j) vin_j = pb[PBIDX(in_j, slot, i)];
+      if (has_k) vin_k = pb[PBIDX(in_k, slot, i)];
       if (pos + 1 < b1) {
         cur_n = in[pos + 1];
-        if (has_j) vj_n = pb[PBIDX(in_j, slot, i + 1)];
-        if (has_k) vk_n = pb[PBIDX(in_k, slot, i + 1)];
+        if (has_j) prefetch_l1(&pb[PBIDX(in_j, slot, i + 1)]);
+        if (has_k) prefetch_l1(&pb[PBIDX(in_k, slot, i + 1)]);
       }
       uint4 vout = make_uint4(0, 0, 0, 0);
 
