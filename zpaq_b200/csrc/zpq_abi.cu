@@ -67,7 +67,7 @@ struct zpq_ctx {
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
   int wave_variant = 9;        // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps
-  int dec_variant = 7;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7) slot-scheduled hashes
+  int dec_variant = 15;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7 or 15) slot-scheduled hashes, bit 3 (15) MATCH in warp A
   bool wave_prof = false;      // ZPQ_WAVE_PROF=1: per-role warp cycles of the wavefront encoder to stderr
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
 };
@@ -360,7 +360,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
                 const uint64_t room6 = ZPQ_SMEM_MAX - (uint64_t)zpq_dec6_static_smem();
                 const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room6 / (pw + (uint64_t)zpq_dec6_ctrl_bytes())));
                 int dv = ctx->dec_variant;
-                if (dv & 4) for (int k = first; k < first + cnt; ++k) if (!models[jobs[wave[k]].model].hplan.ok) { dv &= 3; break; }
+                if (dv & 4) for (int k = first; k < first + cnt; ++k) if (!models[jobs[wave[k]].model].hplan.ok) { dv &= 3; break; }   // 7 / 15 need the hash plan
                 CK(zpq_launch_dec6(&Ak, cnt, ctx->sm_count, teams, (int)pw, sig, dv, st), "zpq_dec_kernel6 launch");
               }
               else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, sig, st), "zpq_code_kernel2 launch");
@@ -483,7 +483,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (const char* gs = getenv("ZPQ_GROUP")) { const int v = atoi(gs); if (v >= 1 && v <= 32) ctx->wave_group = v; }
   if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
   if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 15) ctx->wave_variant = v; }
-  if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if ((v >= 0 && v <= 3) || v == 7) ctx->dec_variant = v; }
+  if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if ((v >= 0 && v <= 3) || v == 7 || v == 15) ctx->dec_variant = v; }
   if (const char* wp = getenv("ZPQ_WAVE_PROF")) ctx->wave_prof = atoi(wp) != 0;
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }

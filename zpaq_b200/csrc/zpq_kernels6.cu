@@ -59,7 +59,8 @@ __host__ __device__ constexpr int sig_count(unsigned long long sig, int upto, un
 // V bit 0: CM / CONST components live in warp A, which requests both candidate entries of the next bit
 //          while it waits for the decoder;
 // V bit 1: warp B requests both candidate MIX / SSE rows of the next bit at the top of the current bit;
-// V bit 2: context hashes from the slot-scheduled plan (ZHashPlan) instead of lane-by-lane interpretation.
+// V bit 2: context hashes from the slot-scheduled plan (ZHashPlan) instead of lane-by-lane interpretation;
+// V bit 3: the MATCH component lives in warp A too (its byte-boundary search runs in A's slack, off warp B's critical path).
 template <unsigned long long SIG, int V>
 __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, const int pw_bytes, const int nteams) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
     u32* gtab = nullptr; u8* ht = nullptr;
     if (lane < n) {
       const ZComp cd = ZM->comp[lane];
-      const bool hashc = cd.type == ZT_ICM || cd.type == ZT_ISSE || ((V & 1) && (cd.type == ZT_CM || cd.type == ZT_CONS));
+      const bool hashc = cd.type == ZT_ICM || cd.type == ZT_ISSE || ((V & 1) && (cd.type == ZT_CM || cd.type == ZT_CONS)) ||
+                         ((V & 8) && cd.type == ZT_MATCH);
       if ((role == 0) == hashc) {
         type = cd.type; a1 = cd.a1; a2 = cd.a2; a3 = cd.a3; a4 = cd.a4; a5 = cd.a5;
         cm_mask = cd.cm_mask; ht_mask = cd.ht_mask; limit = cd.limit; level = ZM->fast.level[lane];
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
       u32 bh = 0, v0 = 0, v1 = 0; int xj = 0;
       u32 cxa = 0, cand0 = 0, cand1 = 0; bool cand = false; int ylast = 0;
+      u32 ma = 0, mb = 0, mpos = 0, mbit = 0, mpred = 0, mc = 0, mdt = 0;      // MATCH state (V bit 3)
       const bool hashl = type == ZT_ICM || type == ZT_ISSE;
       const int nlev = (int)ZM->fast.nlev;
       bool abort = false;
@@ -173,7 +176,14 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
             v0 = cand ? (ylast ? cand1 : cand0) : gtab[cxa];
             p = t_stretch(S, v0 >> 17);
           }
-          if ((V & 1) ? hashl : mine) {
+          if ((V & 8) && type == ZT_MATCH) {
+            if (ma == 0) p = 0;
+            else {
+              mc = (mpred >> (7 - mbit)) & 1u;
+              p = t_stretch(S, (u32)((int)mdt * (1 - 2 * (int)mc)) & 32767u);        // mdt = dt2k[ma] = 2048 / ma
+            }
+          }
+          if ((V & 1) ? hashl : (mine && type != ZT_MATCH)) {
             if (nib) d_find(ht, ht_mask, (int)a1 + 2, h + 16u * (u32)c8, row, row_off);
             bh = row_get(row, hmap4 & 15);
             if (type == ZT_ISSE) {
@@ -225,7 +235,26 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
             gtab[cxa] = v0 + (prod & 0xfffffc00u) + (count < limit ? 1u : 0u);
             ylast = y;
           }
-          if ((V & 1) ? hashl : mine) {
+          if ((V & 8) && type == ZT_MATCH) {
+            // MATCH update (libzpaq.cpp:1990-2008); h is still the hash as of the previous byte here (gotcha 6)
+            if ((int)mc != y) ma = 0;
+            if (++mbit == 8) {
+              mbit = 0;
+              ht[mpos] = (u8)((c8 * 2 + y) & 255);
+              mpos = (mpos + 1) & ht_mask;
+              u32* idx = gtab + (h & cm_mask);
+              if (ma == 0) {
+                mb = mpos - *idx;
+                if (mb & ht_mask)
+                  while (ma < 255 && ht[(mpos - ma - 1) & ht_mask] == ht[(mpos - ma - mb - 1) & ht_mask]) ++ma;
+              }
+              else ma += (ma < 255);
+              *idx = mpos;
+              mpred = ht[(mpos - mb) & ht_mask];
+              mdt = ma ? 2048u / ma : 0u;
+            }
+          }
+          if ((V & 1) ? hashl : (mine && type != ZT_MATCH)) {
             const u32 nx = ((u32)S.ns[bh] >> (8 * y)) & 255u;
             row_set(row, hmap4 & 15, nx);
             if (type == ZT_ISSE) {
@@ -238,7 +267,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
             }
           }
           const int c8n = c8 * 2 + y;
-          if (((V & 1) ? hashl : mine) && (c8n >= 256 || (c8n >= 16 && c8n < 32))) *reinterpret_cast<uint4*>(ht + row_off) = row;
+          if (((V & 1) ? hashl : (mine && type != ZT_MATCH)) && (c8n >= 256 || (c8n >= 16 && c8n < 32))) *reinterpret_cast<uint4*>(ht + row_off) = row;
           if (c8n >= 256) BYTE_END(c8n - 256);
           else {
             c8 = c8n;
@@ -533,11 +562,12 @@ extern "C" cudaError_t zpq_launch_dec6(const ZKernelArgs* a, int nblk, int sm_co
   int ctas = (nblk + teams - 1) / teams;
   if (ctas > sm_count) ctas = sm_count;
   const int th = teams * 64;
-  switch (variant & 7) {
+  switch (variant & 15) {
     case 1: return launch6v<1>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 2: return launch6v<2>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 3: return launch6v<3>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 7: return launch6v<7>(a, ctas, th, smem, pw_bytes, teams, sig, st);
+    case 15: return launch6v<15>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     default: return launch6v<0>(a, ctas, th, smem, pw_bytes, teams, sig, st);
   }
 }
