@@ -8,9 +8,10 @@ import pytest
 import oraclepy as O
 from util import ROOT
 
-B200 = os.path.join(ROOT, "oracle", "_ref", "zpaq_b200")
+# ZPQ_CLI_B200 / ZPQ_CLI_STREAM: set by tools/simt (pre-flight without a GPU) to the same programs linked against the emulator build
+B200 = os.environ.get("ZPQ_CLI_B200", os.path.join(ROOT, "oracle", "_ref", "zpaq_b200"))
 REF = os.path.join(ROOT, "oracle", "_ref", "zpaq_ref")
-STREAM = os.path.join(ROOT, "oracle", "_ref", "shim_stream")
+STREAM = os.environ.get("ZPQ_CLI_STREAM", os.path.join(ROOT, "oracle", "_ref", "shim_stream"))
 need_cli = pytest.mark.skipif(not (os.path.exists(B200) and os.path.exists(REF)), reason="CLI binaries not built (make -C oracle cli)")
 
 

@@ -98,6 +98,11 @@ def main():
         exe = os.path.join(OUT, "zpaq_simt")
         subprocess.check_call(["g++", "-pthread", "-o", exe] + need + ["-L", OUT, "-lzpq_simt", "-Wl,-rpath," + OUT])
         print("built", exe)
+    need = [os.path.join(ref, f) for f in ("shim_stream.o", "libzpaq_shim.o", "libzpaq_renamed.o")]
+    if all(os.path.exists(f) for f in need):
+        exe = os.path.join(OUT, "shim_stream_simt")
+        subprocess.check_call(["g++", "-pthread", "-o", exe] + need + ["-L", OUT, "-lzpq_simt", "-Wl,-rpath," + OUT])
+        print("built", exe)
 
 
 if __name__ == "__main__":

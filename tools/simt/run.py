@@ -32,7 +32,9 @@ def main():
         g.smoke()
     elif what == "pytest":
         import pytest
-        sys.exit(pytest.main(["-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", os.path.join(ROOT, "tests")] + sys.argv[2:]))
+        sys.path.insert(0, HERE)
+        os.environ["PYTHONPATH"] = HERE + os.pathsep + os.environ.get("PYTHONPATH", "")      # xdist workers load the plugin too
+        sys.exit(pytest.main(["-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "-p", "simt_plugin", os.path.join(ROOT, "tests")] + sys.argv[2:]))
     elif what == "script":
         sys.argv = sys.argv[2:]
         runpy.run_path(sys.argv[0], run_name="__main__")

@@ -191,8 +191,7 @@ void compress(Reader* in, Writer* out, const char* method, const char* filename,
       const int n = in->read((char*)sb->data(), (int)block);
       if (n <= 0) { delete sb; more = false; break; }
       sb->resize(n);
-      bufs.push_back(sb);
-      if ((size_t)n < block) more = false;      // short read = end of input (Reader::read contract, libzpaq.h:864)
+      bufs.push_back(sb);                       // one block per read() call, short or not, exactly as the reference cuts them
     }
     std::vector<Req> reqs(bufs.size());
     std::vector<char> on_gpu(bufs.size(), 0);
@@ -388,6 +387,7 @@ void decompress(Reader* in, Writer* out) {
 
 void Decompresser::readSegmentEnd(char* sha1string) {
   DState* S = dstate(this);
+  if (decode_state == FIRSTSEG) *S = DState();      // no decompress() in this block yet: whatever the table holds is an older object's
   if (S->gpu && S->have_plain && state == DATA) {
     // the segment's coded bytes (through their four zeros) are already consumed: nothing to skip, but as in the
     // reference no further decompress() may follow in this block
