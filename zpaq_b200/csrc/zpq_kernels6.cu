@@ -60,6 +60,7 @@ __host__ __device__ constexpr int sig_count(unsigned long long sig, int upto, un
 //          while it waits for the decoder;
 // V bit 1: warp B requests both candidate MIX / SSE rows of the next bit at the top of the current bit;
 // V bit 2: context hashes from the slot-scheduled plan (ZHashPlan) instead of lane-by-lane interpretation;
+// V bit 4: warp B keeps the predictions in registers through the steps (shuffles instead of shared-memory round trips);
 // V bit 3: the MATCH component lives in warp A too (its byte-boundary search runs in A's slack, off warp B's critical path).
 template <unsigned long long SIG, int V>
 __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, const int pw_bytes, const int nteams) {
@@ -405,6 +406,11 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
             while (*flagA != seq) { }
             __threadfence_block();
             __syncwarp();
+            // V bit 4: the predictions stay in registers from here on (pv = prediction of component `lane`): a step reads
+            // its inputs with shuffles and its result replaces pv in the owner lane, so the steps need no shared-memory
+            // round trip (store, __syncwarp, load) between them
+            int pv = (V & 16) ? (int)pp[lane] : 0;
+            int pm0 = 0, pm1 = 0, pm2 = 0;                    // mixer outputs (warp-uniform), for the training below
             // ---- remaining steps ----
 #pragma unroll
             for (int s = 0; s < ZPQ_FAST_STEPS; ++s) {
@@ -416,25 +422,34 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
                 if (kind == ZK_ISSE) { /* done by warp A */ }
                 else if (kind == ZK_MIX) {
                   const u32 q = SIG ? (u32)sig_count(SIG, s, ZK_MIX) : d >> 27;
-                  const int x = (int)pp[(sj + lane) & 31];
+                  int x;
+                  if (V & 16) x = sj == 0 ? pv : __shfl_sync(FULL, pv, (sj + lane) & 31);      // sj is warp-uniform
+                  else x = (int)pp[(sj + lane) & 31];
                   const int w = q == 0 ? mixw0 : (q == 1 ? mixw1 : mixw2);
                   if (q == 0) mixx0 = x; else if (q == 1) mixx1 = x; else mixx2 = x;
                   const int sum = __reduce_add_sync(FULL, lane < sk ? (w >> 8) * x : 0);
-                  if (lane == owner) { p = clamp2k(sum >> 8); pp[lane] = (short)p; }
-                  __syncwarp();
+                  if (V & 16) {
+                    const int pu = clamp2k(sum >> 8);              // the reduction is warp-uniform: every lane has the output
+                    if (q == 0) pm0 = pu; else if (q == 1) pm1 = pu; else pm2 = pu;
+                    if (lane == owner) { p = pu; pv = pu; }
+                  } else {
+                    if (lane == owner) { p = clamp2k(sum >> 8); pp[lane] = (short)p; }
+                    __syncwarp();
+                  }
                 }
                 else if (kind == ZK_MIX2) {
-                  const int pj = (int)pp[sj], pk = (int)pp[sk & 31];
+                  const int pj = (V & 16) ? __shfl_sync(FULL, pv, sj) : (int)pp[sj];
+                  const int pk = (V & 16) ? __shfl_sync(FULL, pv, sk & 31) : (int)pp[sk & 31];
                   if (lane == owner) {
                     xj = pj; xk = pk;
                     const int w = (int)v0;
                     p = (w * pj + (65536 - w) * pk) >> 16;
-                    pp[lane] = (short)p;
+                    if (V & 16) pv = p; else pp[lane] = (short)p;
                   }
-                  __syncwarp();
+                  if (!(V & 16)) __syncwarp();
                 }
                 else if (kind == ZK_SSE) {
-                  const int pj = (int)pp[sj];
+                  const int pj = (V & 16) ? __shfl_sync(FULL, pv, sj) : (int)pp[sj];
                   int pq = min(max(pj + 992, 0), 1983);
                   const int wt = pq & 63;
                   pq >>= 6;
@@ -443,19 +458,20 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
                   if (lane == owner) {
                     p = t_stretch(S, (u32)(((int)(q0 >> 10) * (64 - wt) + (int)(q1 >> 10) * wt) >> 13));
                     if (wt >> 5) { cxt += (u32)pq + 1u; v0 = q1; } else { cxt += (u32)pq; v0 = q0; }
-                    pp[lane] = (short)p;
+                    if (V & 16) pv = p; else pp[lane] = (short)p;
                   }
-                  __syncwarp();
+                  if (!(V & 16)) __syncwarp();
                 }
                 else {   // ZK_AVG
-                  const int pj = (int)pp[sj], pk = (int)pp[sk & 31];
+                  const int pj = (V & 16) ? __shfl_sync(FULL, pv, sj) : (int)pp[sj];
+                  const int pk = (V & 16) ? __shfl_sync(FULL, pv, sk & 31) : (int)pp[sk & 31];
                   const int wt = (int)((d >> 19) & 255u);
-                  if (lane == owner) { p = (pj * wt + pk * (256 - wt)) >> 8; pp[lane] = (short)p; }
-                  __syncwarp();
+                  if (lane == owner) { p = (pj * wt + pk * (256 - wt)) >> 8; if (V & 16) pv = p; else pp[lane] = (short)p; }
+                  if (!(V & 16)) __syncwarp();
                 }
               }
             }
-            const int pfin = (int)pp[n - 1];
+            const int pfin = (V & 16) ? __shfl_sync(FULL, pv, n - 1) : (int)pp[n - 1];
             const int y = dec6_bit(C, (u32)t_squash(S, pfin) * 2u + 1u);
             if (C.status != ST_OK) { status = C.status; SEND(2, 0); failed = true; break; }
             SEND(0, y);
@@ -495,8 +511,12 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
 #pragma unroll
             for (int q = 0; q < ZPQ_FAST_MIX; ++q)
               if (q < NMIXC && q < nmix) {
-                const int e0 = ((y * 32767 - t_squash(S, p)) * (int)mix_rate[q]) >> 4;
-                const int err = __shfl_sync(FULL, e0, (int)mix_owner[q]);
+                int err;
+                if (V & 16) err = ((y * 32767 - t_squash(S, q == 0 ? pm0 : (q == 1 ? pm1 : pm2))) * (int)mix_rate[q]) >> 4;   // uniform
+                else {
+                  const int e0 = ((y * 32767 - t_squash(S, p)) * (int)mix_rate[q]) >> 4;
+                  err = __shfl_sync(FULL, e0, (int)mix_owner[q]);
+                }
                 const int w = q == 0 ? mixw0 : (q == 1 ? mixw1 : mixw2);
                 const int x = q == 0 ? mixx0 : (q == 1 ? mixx1 : mixx2);
                 if (lane < (int)mix_m[q]) mix_tab[q][mixbase[q] + lane] = clamp512k(w + ((err * x + (1 << 12)) >> 13));
@@ -562,12 +582,13 @@ extern "C" cudaError_t zpq_launch_dec6(const ZKernelArgs* a, int nblk, int sm_co
   int ctas = (nblk + teams - 1) / teams;
   if (ctas > sm_count) ctas = sm_count;
   const int th = teams * 64;
-  switch (variant & 15) {
+  switch (variant & 31) {
     case 1: return launch6v<1>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 2: return launch6v<2>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 3: return launch6v<3>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 7: return launch6v<7>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     case 15: return launch6v<15>(a, ctas, th, smem, pw_bytes, teams, sig, st);
+    case 31: return launch6v<31>(a, ctas, th, smem, pw_bytes, teams, sig, st);
     default: return launch6v<0>(a, ctas, th, smem, pw_bytes, teams, sig, st);
   }
 }
