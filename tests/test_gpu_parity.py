@@ -34,10 +34,10 @@ def test_method_parity(kctx, method, kind):
         _roundtrip(ctx, hdr, ps)
 
 
-@pytest.mark.parametrize("env,values", [("ZPQ_DEC_VARIANT", ["0", "1", "2", "3", "7", "15", "31"]), ("ZPQ_WAVE_VARIANT", ["0", "1", "2", "3", "4", "5", "8", "9"])])
+@pytest.mark.parametrize("env,values", [("ZPQ_DEC_VARIANT", ["0", "1", "2", "3", "7", "15", "31"]), ("ZPQ_WAVE_VARIANT", ["0", "1", "2", "3", "4", "5", "8", "9", "24", "25"])])
 def test_kernel_variants_are_bit_exact(env, values):
     """Every switchable variant of the production kernels (two-warp decoder: candidate entries / rows, slot-scheduled
-    hashes, MATCH in warp A, register-resident predictions in warp B; wavefront encoder: byte-ahead MIX rows, split launches, mixers as component threads, byte-batched MIX warps) codes the same bytes as the oracle."""
+    hashes, MATCH in warp A, register-resident predictions in warp B; wavefront encoder: byte-ahead MIX rows, split launches, mixers as component threads, byte-batched MIX warps, nibble-unrolled ICM / ISSE loop) codes the same bytes as the oracle."""
     import os
     payloads = [O.gen_block(kind, 500 + kind, 6000 + 111 * kind) for kind in (0, 1, 2, 3)]
     for v in values:

@@ -66,7 +66,7 @@ struct zpq_ctx {
   uint64_t launches = 0;
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
-  int wave_variant = 9;        // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps
+  int wave_variant = 25;       // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps, bit 4 nibble-unrolled ICM / ISSE loop
   int dec_variant = 31;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7 or 15) slot-scheduled hashes, bit 3 (15) MATCH in warp A, bit 4 (31) register-resident predictions in warp B
   bool wave_prof = false;      // ZPQ_WAVE_PROF=1: per-role warp cycles of the wavefront encoder to stderr
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
@@ -314,6 +314,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           Wv.chunk_bytes = CB; Wv.ncs = ncs; Wv.ngroups = ngroups; Wv.gsize = GS;
           Wv.prof = nullptr;
           // ZPQ_WAVE_VARIANT bit 2: mixers as component threads, when every MIX of every model in the launch qualifies
+          Wv.hash_loop = (ctx->wave_variant & 16) ? 1 : 0;       // bit 4: nibble-unrolled ICM / ISSE loop
           Wv.mix_batch = (ctx->wave_variant & 8) ? 1 : 0;        // bit 3: byte-batched MIX warps
           Wv.mix_threads = (ctx->wave_variant & 4) ? 1 : 0;
           for (int k = first; k < first + cnt && Wv.mix_threads; ++k) {
@@ -482,7 +483,7 @@ int zpq_create(int device, zpq_ctx** out) {
   ctx->device = device;
   if (const char* gs = getenv("ZPQ_GROUP")) { const int v = atoi(gs); if (v >= 1 && v <= 32) ctx->wave_group = v; }
   if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
-  if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 15) ctx->wave_variant = v; }
+  if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 31) ctx->wave_variant = v; }
   if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if ((v >= 0 && v <= 3) || v == 7 || v == 15 || v == 31) ctx->dec_variant = v; }
   if (const char* wp = getenv("ZPQ_WAVE_PROF")) ctx->wave_prof = atoi(wp) != 0;
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }

@@ -251,6 +251,7 @@ struct ZWaveArgs {
   int wave, chunk_bytes, ncs, ngroups;   // ncs = component slots per block = max components + 1 (coder)
   int gsize;                             // blocks per group (= active lanes of a component warp), <= 32
   unsigned long long* prof;              // optional [32][2]: cycles and warp count per role (ZPQ_WAVE_PROF=1), else null
+  int hash_loop;                         // 1: ICM / ISSE component threads run the nibble-unrolled loop (zpq_kernels5.cu)
   int mix_batch;                         // 1: MIX warps mix the eight bits of a byte together (full-mask mixers; zpq_kernels5.cu)
   int mix_threads;                       // 1: every MIX of the launch has a full c8 mask and >= 256 weight sets and is coded
                                          // by a component thread (eight independent rows per byte); 0: one warp per (block, MIX)

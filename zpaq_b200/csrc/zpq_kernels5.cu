@@ -205,6 +205,118 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
       cs[5] = (u32)hist; cs[6] = (u32)(hist >> 32);
       return 11;
     }
+    if (is_hash && W.hash_loop) {
+      // ---------------- ICM / ISSE: the loop of the longest chain, written out per nibble ----------------
+      // Same operations as the generic loop below (which stays the path of the other component types and the A/B
+      // reference for this one: ZPQ_WAVE_VARIANT bit 4 off), but with the two nibbles and their four bits unrolled:
+      // the bit index is a constant (vector lane extraction, "last bit of the nibble" tests and the type switches fold
+      // away) and the slot inside the hash row is a running value (1, 1y, 1yy, 1yyy).
+      const bool isse = type == ZT_ISSE;
+      uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
+      uint4 pf0 = row, pf1 = row, pf2 = row; u32 pf_h0 = 0; bool pf_valid = false;
+      u32 cur_n = in[b0];
+      for (int pos = b0; pos < b1; ++pos) {
+        const u32 cur = cur_n;
+        const int i = pos - b0;
+        uint4 vin_j = make_uint4(0, 0, 0, 0);
+        if (isse) vin_j = pb[PBIDX(a2, slot, i)];
+        const bool more = pos + 1 < b1;
+        if (more) {
+          cur_n = in[pos + 1];
+          if (isse) prefetch_l1(&pb[PBIDX(a2, slot, i + 1)]);
+        }
+        uint4 vout = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          if (nb == 1) {
+            const u64 hs = (hist << 8) | (u64)cur;
+            if (cur == dist_byte) dist_last = (u32)(-(pos + 1));
+            h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
+            hist = hs;
+          }
+          // Predictor::find (libzpaq.cpp:2072-2088) on rows requested one nibble ago
+          const u32 c8 = nb == 0 ? 1u : (0x10u | (cur >> 4));
+          const u32 cx = h + 16u * c8;
+          const u32 chk = (cx >> (a1 + 2)) & 255u;
+          const u32 h0 = (cx * 16u) & ht_mask;
+          uint4 r0, r1, r2;
+          if (pf_valid && pf_h0 == h0) { r0 = pf0; r1 = pf1; r2 = pf2; }
+          else {
+            r0 = *reinterpret_cast<const uint4*>(ht + h0);
+            r1 = *reinterpret_cast<const uint4*>(ht + (h0 ^ 16u));
+            r2 = *reinterpret_cast<const uint4*>(ht + (h0 ^ 32u));
+          }
+          if ((r0.x & 255u) == chk) { row = r0; row_off = h0; }
+          else if ((r1.x & 255u) == chk) { row = r1; row_off = h0 ^ 16u; }
+          else if ((r2.x & 255u) == chk) { row = r2; row_off = h0 ^ 32u; }
+          else {
+            const u32 q0 = (r0.x >> 8) & 255u, q1 = (r1.x >> 8) & 255u, q2 = (r2.x >> 8) & 255u;
+            if (q0 <= q1 && q0 <= q2) row_off = h0;
+            else if (q1 < q2) row_off = h0 ^ 16u;
+            else row_off = h0 ^ 32u;
+            row = make_uint4(chk, 0, 0, 0);
+          }
+          const u32 ncx = nb == 0 ? (h + 16u * (0x10u | (cur >> 4))) : (h_next + 16u);
+          const u32 nh0 = (ncx * 16u) & ht_mask;
+          pf_valid = ((nh0 ^ row_off) & ~63u) != 0u && (nb == 0 || more);
+          if (pf_valid) {
+            pf_h0 = nh0;
+            pf0 = *reinterpret_cast<const uint4*>(ht + nh0);
+            pf1 = *reinterpret_cast<const uint4*>(ht + (nh0 ^ 16u));
+            pf2 = *reinterpret_cast<const uint4*>(ht + (nh0 ^ 32u));
+          }
+          // the four bits of the nibble; hsl = slot inside the row = hmap4 & 15
+          const u32 nibv = nb == 0 ? (cur >> 4) : (cur & 15u);
+          u32 hsl = 1u;
+          u32 bh = row_get(row, 1);
+          u32 t0, t1 = 0;                                   // table entry of the current bit (ISSE: weight pair)
+          if (isse) { const uint2 w = *reinterpret_cast<const uint2*>(gtab + bh * 2); t0 = w.x; t1 = w.y; }
+          else t0 = gtab[bh];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int bit = nb * 4 + b;
+            const int y = (int)((nibv >> (3 - b)) & 1u);
+            // entry of the NEXT bit of this nibble (its slot is input data), requested before this bit's arithmetic
+            const u32 hsn = hsl * 2u + (u32)y;
+            u32 nbh = 0, n0 = 0, n1 = 0;
+            if (b < 3) {
+              nbh = row_get(row, (int)hsn);
+              if (isse) { const uint2 wn = *reinterpret_cast<const uint2*>(gtab + nbh * 2); n0 = wn.x; n1 = wn.y; }
+              else n0 = gtab[nbh];
+            }
+            int pr;
+            u32 u0, u1 = 0;
+            if (isse) {
+              const int xj = vget(vin_j, bit);
+              pr = clamp2k(((int)t0 * xj + (int)t1 * 64) >> 16);
+              const int err = y * 32767 - t_squash(S, pr);
+              u0 = (u32)clamp512k((int)t0 + ((err * xj + (1 << 12)) >> 13));
+              u1 = (u32)clamp512k((int)t1 + ((err + 16) >> 5));
+              *reinterpret_cast<uint2*>(gtab + bh * 2) = make_uint2(u0, u1);
+            } else {
+              pr = t_stretch(S, t0 >> 8);
+              u0 = t0 + (u32)(((int)(y * 32767 - (int)(t0 >> 8))) >> 2);
+              gtab[bh] = u0;
+            }
+            row_set(row, (int)hsl, ((u32)S.ns[bh] >> (8 * y)) & 255u);
+            vset(vout, bit, pr);
+            if (b < 3) {
+              // the next bit's entry is the one just trained when both slots hold the same bit-history state
+              const bool same = nbh == bh;
+              t0 = same ? u0 : n0; t1 = same ? u1 : n1;
+              bh = nbh; hsl = hsn;
+            }
+          }
+          *reinterpret_cast<uint4*>(ht + row_off) = row;
+        }
+        pb[PBIDX(c, slot, i)] = vout;
+        h = h_next;
+      }
+      cs[0] = h; cs[1] = st[0]; cs[2] = st[1]; cs[3] = st[2]; cs[4] = st[3];
+      cs[5] = (u32)hist; cs[6] = (u32)(hist >> 32); cs[7] = dist_last;
+      cs[8] = ma; cs[9] = mb; cs[10] = mpos; cs[11] = mpred;
+      return (int)type;
+    }
     int p = (type == ZT_CONS) ? ((int)a1 - 128) * 4 : 0;
     uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
     uint4 pf0 = row, pf1 = row, pf2 = row; u32 pf_h0 = 0; bool pf_valid = false;
