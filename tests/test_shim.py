@@ -28,7 +28,7 @@ def _run(exe, args, cwd, log=False):
     env = dict(os.environ)
     if log:
         env["ZPQ_SHIM_LOG"] = "1"       # one stderr line per routed call: proves which path ran
-    r = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=900, env=env)
+    r = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=int(os.environ.get("ZPQ_TEST_TIMEOUT", "900")), env=env)
     return r.returncode, r.stdout + r.stderr
 
 
