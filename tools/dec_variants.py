@@ -7,7 +7,7 @@ import oraclepy as O, zpaq_b200 as Z
 
 nblk = int(sys.argv[1]) if len(sys.argv) > 1 else 1029
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
-variants = [int(v) for v in (sys.argv[3] if len(sys.argv) > 3 else "0,1,2,3").split(",")]
+variants = [int(v) for v in (sys.argv[3] if len(sys.argv) > 3 else "3,7,15,31").split(",")]
 method = sys.argv[4] if len(sys.argv) > 4 else "5"
 pays = [O.gen_block(1, 777 + i, n) for i in range(nblk)]
 hdr = Z.model_from_method(method, pays[0])
