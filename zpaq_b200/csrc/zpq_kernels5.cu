@@ -317,6 +317,75 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
       cs[8] = ma; cs[9] = mb; cs[10] = mpos; cs[11] = mpred;
       return (int)type;
     }
+    if (type == ZT_SSE && W.hash_loop) {
+      // ---------------- SSE: the eight bits of a byte unrolled (same switch as the ICM / ISSE loop above) ----------------
+      // Same operations as the generic loop below; with a constant bit index c8, the input extraction and the
+      // "is there a next bit in this byte" tests are free, and the two interpolation buckets of the NEXT bit (known from
+      // input data and from the input prediction that is already here) are requested before this bit's arithmetic.
+      u32 cur_n = in[b0];
+      for (int pos = b0; pos < b1; ++pos) {
+        const u32 cur = cur_n;
+        const int i = pos - b0;
+        const uint4 vin_j = pb[PBIDX(a2, slot, i)];
+        if (pos + 1 < b1) {
+          cur_n = in[pos + 1];
+          prefetch_l1(&pb[PBIDX(a2, slot, i + 1)]);
+        }
+        uint4 vout = make_uint4(0, 0, 0, 0);
+        u32 q0 = 0, q1 = 0, key = 0;
+        {
+          const u32 rb = ((h + 1u) * 32u) & cm_mask;
+          key = rb + (u32)(min(max(vget(vin_j, 0) + 992, 0), 1983) >> 6);
+          q0 = gtab[key]; q1 = gtab[key + 1u];
+        }
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+          const int y = (int)((cur >> (7 - bit)) & 1u);
+          if ((bit & 3) == 0) {
+            // rows of the bits after next: into L2 now (their addresses are input data)
+#pragma unroll
+            for (int k = 2; k <= 5; ++k)
+              if (bit + k < 8) prefetch_l2(gtab + (((h + ((0x100u | cur) >> (8 - bit - k))) * 32u) & cm_mask));
+            if (bit == 4) {
+              const u64 hs = (hist << 8) | (u64)cur;
+              if (cur == dist_byte) dist_last = (u32)(-(pos + 1));
+              h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
+              hist = hs;
+            }
+          }
+          const int pin = min(max(vget(vin_j, bit) + 992, 0), 1983);
+          const int wt = pin & 63;
+          // buckets of the next bit of this byte
+          u32 nkey = 0, n0 = 0, n1 = 0;
+          if (bit < 7) {
+            const u32 rbn = ((h + ((0x100u | cur) >> (7 - bit))) * 32u) & cm_mask;
+            nkey = rbn + (u32)(min(max(vget(vin_j, bit + 1) + 992, 0), 1983) >> 6);
+            n0 = gtab[nkey]; n1 = gtab[nkey + 1u];
+          }
+          const int pr = t_stretch(S, (u32)(((int)(q0 >> 10) * (64 - wt) + (int)(q1 >> 10) * wt) >> 13));
+          const u32 cxt = key + (u32)(wt >> 5);                 // the nearer bucket is trained (libzpaq.cpp:1930-1939)
+          const u32 v0 = (wt >> 5) ? q1 : q0;
+          const u32 count = v0 & 0x3ffu;
+          const int err = y * 32767 - (int)(v0 >> 17);
+          const u32 prod = (u32)err * ((u32)S.dt[count] * 2u);
+          const u32 up = v0 + (prod & 0xfffffc00u) + (count < limit ? 1u : 0u);
+          gtab[cxt] = up;
+          vset(vout, bit, pr);
+          if (bit < 7) {
+            // a prefetched bucket that was just trained takes the trained value
+            if (nkey == cxt) n0 = up;
+            if (nkey + 1u == cxt) n1 = up;
+            key = nkey; q0 = n0; q1 = n1;
+          }
+        }
+        pb[PBIDX(c, slot, i)] = vout;
+        h = h_next;
+      }
+      cs[0] = h; cs[1] = st[0]; cs[2] = st[1]; cs[3] = st[2]; cs[4] = st[3];
+      cs[5] = (u32)hist; cs[6] = (u32)(hist >> 32); cs[7] = dist_last;
+      cs[8] = ma; cs[9] = mb; cs[10] = mpos; cs[11] = mpred;
+      return (int)type;
+    }
     int p = (type == ZT_CONS) ? ((int)a1 - 128) * 4 : 0;
     uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
     uint4 pf0 = row, pf1 = row, pf2 = row; u32 pf_h0 = 0; bool pf_valid = false;
