@@ -346,6 +346,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "alg_bytes_per_input_byte": balg, "kernel": "zpq_wave_kernel (encode, 525 launches per step) + zpq_dec_kernel6 (decode)",
+                         "kernel_variants": {"ZPQ_WAVE_VARIANT": os.environ.get("ZPQ_WAVE_VARIANT", "25 (default)"),
+                                             "ZPQ_DEC_VARIANT": os.environ.get("ZPQ_DEC_VARIANT", "31 (default)")},
                          "note": "latency/issue bound, not bandwidth bound (see profiles/ and DESIGN.md section 6)"},
             "cpu_baseline": cpu, "bit_exact_vs_reference": bit_exact, "clocks": clocks,
             "archive_ratio": r["arc_bytes"] / nbytes, "setup_s": gen_s,
