@@ -9,6 +9,7 @@ The translation is textual and touches only what g++ cannot parse:
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory")   ->  simt_named_barrier(id, count)
   asm volatile("prefetch.global.L1|L2 [%0];" :: "l"(p))                ->  (void)(p)
   while (cond) { }      (spin on a volatile shared word)               ->  while (cond) { simt_spin(); }
+  for (...; cond;) { if (++spin > SPIN_CAP) ... }   (capped spin)      ->  ... { simt_spin(); if (++spin > SPIN_CAP) ... }
 """
 import os
 import re
@@ -54,6 +55,8 @@ def translate(text, name):
     text, n_bar = re.subn(r'asm volatile\("bar\.sync %0, %1;"\s*::\s*"r"\((.*?)\),\s*"r"\((\d+)\)\s*:\s*"memory"\)', r"simt_named_barrier(\1, \2)", text)
     text, n_pf = re.subn(r'asm volatile\("prefetch\.global\.L[12] \[%0\];"\s*::\s*"l"\((\w+)\)\)', r"(void)(\1)", text)
     text, n_spin = re.subn(r"(while \(.*\)) \{ \}", r"\1 { simt_spin(); }", text)
+    text, n_spin2 = re.subn(r"\{ if \(\+\+(spin_?) > SPIN_CAP\)", r"{ simt_spin(); if (++\1 > SPIN_CAP)", text)     # capped spin loops
+    n_spin += n_spin2
     text = text.replace("__noinline__", "__attribute__((noinline))")
     if "asm" in re.sub(r"//.*", "", text):
         raise SystemExit("%s: untranslated inline asm left" % name)

@@ -26,6 +26,8 @@
 #define S6_CTRL 80                          // per block: short pp[32], flagA, flagB, block index, pad
 #define PAIR_BAR(team) asm volatile("bar.sync %0, %1;" ::"r"((team) + 1), "r"(64) : "memory")
 #define SEQ_MASK 0x1fffffffu
+#define SPIN_CAP (1u << 27)                 // polls of a hand-shake word before the block is given up (seconds, not microseconds)
+#define ST_HUNG (-9)                        // reported as ZPQ_E_CUDA: an internal hand-shake was lost
 
 struct Dec6 {
   u32 low, high, curr;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       u32 ma = 0, mb = 0, mpos = 0, mbit = 0, mpred = 0, mc = 0, mdt = 0;      // MATCH state (V bit 3)
       const bool hashl = type == ZT_ICM || type == ZT_ISSE;
       const int nlev = (int)ZM->fast.nlev;
-      bool abort = false;
+      bool abort = false, hungA = false;
       for (u32 sg = 0; sg < B.nseg && !abort; ++sg) {
         for (;;) {
           // ---- predict ----
@@ -221,7 +223,8 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           }
           // ---- wait for the decoder ----
           u32 msg;
-          while (((msg = *flagB) >> 3) != (seq & SEQ_MASK)) { }
+          // (spin cap: a lost hand-shake becomes an aborted block with status ST_HUNG instead of a hung GPU)
+          for (u32 spin = 0; ((msg = *flagB) >> 3) != (seq & SEQ_MASK);) { if (++spin > SPIN_CAP) { msg = 2u << 1; hungA = true; break; } }
           __threadfence_block();
           seq = (seq + 1) & SEQ_MASK;
           const u32 kind = (msg >> 1) & 3u;
@@ -277,6 +280,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
           }
         }
       }
+      if (hungA && lane == 0) { A.status[blk] = ST_HUNG; A.out_len[blk] = 0; }     // warp B never answered
     } else {
       // ================ warp B: CM, MATCH, CONST, AVG, MIX2, SSE, MIX, arithmetic decoder ================
       constexpr int NMIXC = SIG ? sig_count(SIG, ZPQ_FAST_STEPS, ZK_MIX) : ZPQ_FAST_MIX;     // known from the signature
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
 // Control messages (end of segment, abort) leave the per-bit hand-shake: flagB is a one-word mailbox, so before it is
 // overwritten warp A must have consumed the previous message -- which it has once it published the prediction it is about
 // to wait on (flagA == seq).
-#define SEND_CTRL(kind) do { while (*flagA != seq) { } SEND(kind, 0); } while (0)
+#define SEND_CTRL(kind) do { for (u32 spin_ = 0; *flagA != seq;) { if (++spin_ > SPIN_CAP) break; } SEND(kind, 0); } while (0)
 
       for (u32 sg = 0; sg < B.nseg && status == ST_OK; ++sg) {
         const u64 seg_n = A.seg_len[B.seg_first + sg];
@@ -403,7 +407,9 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
               }
             if (type == ZT_CM || type == ZT_MATCH || type == ZT_CONS) pp[lane] = (short)p;
             // ---- predictions of the hash components ----
-            while (*flagA != seq) { }
+            bool hungB = false;
+            for (u32 spin = 0; *flagA != seq;) { if (++spin > SPIN_CAP) { hungB = true; break; } }
+            if (hungB) { status = ST_HUNG; SEND(2, 0); failed = true; break; }      // warp A never published: give the block up
             __threadfence_block();
             __syncwarp();
             // V bit 4: the predictions stay in registers from here on (pv = prediction of component `lane`): a step reads
