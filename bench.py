@@ -69,37 +69,74 @@ def alg_bytes_per_input_byte(hdr, block_bytes):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled once a second DURING the timed region.  In-process NVML
+    (nvidia_ml_py): a query is microseconds and takes no driver-wide lock for long; spawning nvidia-smi twice a second per
+    rank initialises a driver context each time and measurably disturbs the launch path of the other ranks (the encoder
+    issues ~525 launches per step).  nvidia-smi is only the fallback when NVML cannot be imported."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
         self.reasons = set()
         self.sm_max = None
+        self.how = None
         self._stop_evt = threading.Event()
 
-    def run(self):
+    def _nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                idx = int(ids[self.index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        self.how = "nvml"
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for nm, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(1.0)
+
+    def _smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.how = "nvidia-smi"
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.samples.append(float(out[0]))
                 self.sm_max = float(out[1])
-                for nm, v in zip(names, out[2:]):
+                for (nm, _), v in zip(self.REASONS, out[2:]):
                     if v.strip().lower() == "active":
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop_evt.wait(0.5)
+            self._stop_evt.wait(2.0)
+
+    def run(self):
+        try:
+            self._nvml()
+        except Exception:
+            if not self.samples:
+                self._smi()
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": self.how}
 
 
 def host_threads():
