@@ -44,6 +44,20 @@ def test_cli_links_and_lz77_methods_stay_on_the_cpu_code(tmp_path):
 
 
 @need_cli
+def test_zpaq_extract_of_stored_blocks_needs_no_gpu(tmp_path):
+    """`zpaq x` through the shim's Decompresser::decompress / readSegmentEnd on an archive without context-model blocks
+    (method 1: LZ77, unmodelled): every block is routed to the reference's own decoder, nothing touches the GPU library."""
+    names = _files(tmp_path)
+    rc, out = _run(REF, ["add", "l.zpaq"] + names + ["-method", "1"], tmp_path)
+    assert rc == 0, out
+    rc, out = _run(B200, ["x", "l.zpaq", "-to", "ol", "-threads", "2"], tmp_path, log=True)
+    assert rc == 0, out
+    assert "-> reference CPU code" in out and "-> GPU" not in out, out
+    for n in names:
+        assert (tmp_path / "ol" / n).read_bytes() == (tmp_path / n).read_bytes()
+
+
+@need_cli
 @pytest.mark.gpu
 @pytest.mark.parametrize("method", ["4", "5"])
 def test_zpaq_add_on_gpu_extracts_with_stock_zpaq(tmp_path, method):
