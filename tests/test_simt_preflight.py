@@ -1,0 +1,31 @@
+"""CPU tier: the LOGIC of the production CUDA kernels, checked bit for bit against the oracle on the SIMT emulator
+(tools/simt: the .cu sources compiled with g++, every CUDA thread a fiber).  This is a pre-flight, not the parity gate:
+the `-m gpu` tests on a B200 are.  The emulator build is test infrastructure; nothing in zpaq_b200/ can load it."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+from util import ROOT
+
+SIMT = os.path.join(ROOT, "tools", "simt")
+
+
+@pytest.fixture(scope="module")
+def simt_build():
+    if shutil.which("g++") is None or os.uname().machine != "x86_64":
+        pytest.skip("the emulator needs g++ on x86-64")
+    r = subprocess.run([sys.executable, os.path.join(SIMT, "build.py")], capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        pytest.fail("tools/simt/build.py failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return os.path.join(SIMT, "_build", "libzpq_simt.so")
+
+
+@pytest.mark.timeout(900)
+def test_production_kernels_on_the_emulator(simt_build):
+    env = dict(os.environ, SIMT_WATCHDOG="600")
+    r = subprocess.run([sys.executable, os.path.join(SIMT, "run.py"), "script", os.path.join(ROOT, "tests", "simt_preflight_case.py")],
+                       capture_output=True, text=True, timeout=800, env=env)
+    assert r.returncode == 0 and "simt preflight ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
