@@ -29,6 +29,7 @@
 #include <map>
 #include <string.h>
 #include <stdlib.h>
+#include <ctype.h>
 #include <stdio.h>
 #include <algorithm>
 
@@ -172,13 +173,15 @@ void compressBlock(StringBuffer* in, Writer* out, const char* method, const char
 // then written in order.  Blocks of methods outside the context-model family go to the reference's own code.
 // ------------------------------------------------------------------------------------------------
 void compress(Reader* in, Writer* out, const char* method, const char* filename, const char* comment, bool dosha1) {
+  // block size exponent: up to two decimal digits right after the level character, default 4, at most 11
   int bs = 4;
-  if (method && method[0] && method[1] >= '0' && method[1] <= '9') {
-    bs = method[1] - '0';
-    if (method[2] >= '0' && method[2] <= '9') bs = bs * 10 + method[2] - '0';
-    if (bs > 11) bs = 11;
+  const char* digits = (method && method[0]) ? method + 1 : "";
+  if (isdigit((unsigned char)digits[0])) {
+    bs = digits[0] - '0';
+    if (isdigit((unsigned char)digits[1])) bs = 10 * bs + (digits[1] - '0');
   }
-  const size_t block = ((size_t)0x100000 << bs) - 4096;
+  bs = std::min(bs, 11);
+  const size_t block = ((size_t)1 << (20 + bs)) - 4096;
   size_t max_blocks = 256;
   if (const char* e = getenv("ZPQ_SHIM_BATCH")) { const long v = atol(e); if (v >= 1 && v <= 65536) max_blocks = (size_t)v; }
   max_blocks = std::max<size_t>(1, std::min(max_blocks, ((size_t)2 << 30) / block));
