@@ -150,6 +150,10 @@ struct ZHashSlot { uint32_t lanes, kind; };   // lanes that have an op in the sl
 struct ZHashPlan {
   uint32_t ok, nslots;
   uint8_t last_seg[ZPQ_MAX_LANES];       // index of the lane's last segment (its state receives the final value)
+  uint8_t fold_n[ZPQ_MAX_LANES];         // n+1 for lanes whose recipe is the order-n byte hash (ZWave.fold_n): they take no
+                                         // slots; all of them are folded together from the history register in one
+                                         // predicated 8-step loop
+  uint32_t fold_lanes;                   // those lanes
   alignas(8) ZHashSlot slot[ZPQ_HSLOTS];
   uint32_t w[ZPQ_HSLOTS][32];            // operand word per lane (the flat op word; ZH_SEG: segment index in bits 8-9)
   uint32_t w2[ZPQ_HSLOTS][32];           // ZH_WORD: second word (multiplier, first flag)

@@ -490,6 +490,12 @@ struct PlanEval {      // host mirror of hplan_eval (zpq_kcommon.cuh)
           default: break;
         }
       }
+    for (int l = 0; l < n; ++l)
+      if (P.fold_n[l]) {
+        uint32_t a = 0;
+        for (uint32_t k = 0; k + 1 < P.fold_n[l]; ++k) a = (a + ((uint32_t)(hist >> (8 * k)) & 255u) + 512u) * 773u;
+        acc[l] = a;
+      }
     for (int l = 0; l < n; ++l) { st[l][P.last_seg[l]] = acc[l]; h[l] = acc[l]; }
   }
 };
@@ -505,6 +511,7 @@ void build_hash_plan(ZModel* M) {
   struct Op { uint32_t kind, w, w2; };
   std::vector<std::vector<Op>> ops(n);
   for (int l = 0; l < n; ++l) {
+    if (W.fold_n[l]) { P.fold_n[l] = W.fold_n[l]; P.fold_lanes |= 1u << l; P.last_seg[l] = 0; continue; }   // folded outside the slots
     int k = -1;
     for (uint32_t t = 0; t < W.flat_len[l]; ++t) {
       const uint32_t w = W.flat[l][t], kind = w & 15u;

@@ -172,9 +172,18 @@ __device__ __forceinline__ u32 wave_hash(u32 fold_n1, const u32* __restrict__ op
 // position-modulo source.  `mine_mask` = lanes of this warp that own a component (slots without any of them are skipped),
 // `vc` = the HCOMP byte counter (0 - bytes seen), `ring` = the M ring the bytecode reads old bytes from.
 // Returns the lane's new hash (h_old for a lane that owns nothing).
-__device__ __forceinline__ u32 hplan_eval(const ZHashPlan* __restrict__ P, u32 mine_mask, int lane, u32 last_seg,
+__device__ __forceinline__ u32 hplan_eval(const ZHashPlan* __restrict__ P, u32 mine_mask, int lane, u32 last_seg, u32 fold_n1,
                                           u32 st[ZPQ_FLAT_SEGS], u32 cur, u64 hs, u32 vc, const u8* ring, u32 ring_mask,
                                           u32 dist_last, u32 h_old) {
+  // lanes whose recipe is the order-n byte hash (fold_n1 = n + 1): one predicated 8-step loop for all of them
+  u32 accf = 0;
+  if (__ldg(&P->fold_lanes) & mine_mask) {               // warp-uniform
+#pragma unroll
+    for (u32 k = 0; k < 8; ++k) {
+      const u32 nx = (accf + ((u32)(hs >> (8u * k)) & 255u) + 512u) * 773u;
+      if (k + 1u < fold_n1) accf = nx;
+    }
+  }
   u32 acc = 0, prev_new = 0, prev_old = 0;
   const int ns = (int)P->nslots;
   const uint2* __restrict__ sd = reinterpret_cast<const uint2*>(P->slot);
@@ -230,6 +239,7 @@ __device__ __forceinline__ u32 hplan_eval(const ZHashPlan* __restrict__ P, u32 m
     }
   }
   if (!((mine_mask >> lane) & 1u)) return h_old;
+  if (fold_n1) { st[0] = accf; return accf; }
   if (last_seg == 0u) st[0] = acc; else if (last_seg == 1u) st[1] = acc; else if (last_seg == 2u) st[2] = acc; else st[3] = acc;
   return acc;
 }

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
     const ZHashPlan* __restrict__ HP = &ZM->hplan;
     const u32 mine_mask = __ballot_sync(FULL, mine);
     const u32 hp_last = (lane < n) ? (u32)HP->last_seg[lane] : 0u;
+    const u32 hp_fold = (lane < n) ? (u32)HP->fold_n[lane] : 0u;
     const u32 tabw = wbase + ((lane < n) ? ZM->fast.smem_off[lane] : 0u) / 4u;
     if (role == 0) {
       if (type == ZT_ICM || type == ZT_ISSE) { /* tables initialised below by the whole warp */ }
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel6(const ZKernelArgs A, c
       vm_c -= 1; mring[vm_c & mmask] = (u8)bv_;          /* both warps write the same value */       \
       hist = (hist << 8) | (u64)bv_;                                                                 \
       if (mine && bv_ == dist_byte) dist_last = vm_c;                                                \
-      if (V & 4) h = hplan_eval(HP, mine_mask, lane, hp_last, st, bv_, hist, vm_c, mring, mmask, dist_last, h);   \
+      if (V & 4) h = hplan_eval(HP, mine_mask, lane, hp_last, hp_fold, st, bv_, hist, vm_c, mring, mmask, dist_last, h);   \
       else if (mine) h = flat_eval(fops, flen, st, bv_, hist, (int)(0u - vm_c) - 1, mring, dist_last, mmask);     \
       hmap4 = 1; c8 = 1;                                                                             \
     } while (0)
