@@ -29,3 +29,13 @@ def test_production_kernels_on_the_emulator(simt_build):
     r = subprocess.run([sys.executable, os.path.join(SIMT, "run.py"), "script", os.path.join(ROOT, "tests", "simt_preflight_case.py")],
                        capture_output=True, text=True, timeout=800, env=env)
     assert r.returncode == 0 and "simt preflight ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.timeout(600)
+def test_emulator_selftest():
+    """The emulator's own semantics (shuffles, ballots, reductions, barriers, named barriers, spin hand-shakes between
+    warps, exited lanes, atomics) against closed-form answers, independent of the product kernels."""
+    if shutil.which("g++") is None or os.uname().machine != "x86_64":
+        pytest.skip("the emulator needs g++ on x86-64")
+    r = subprocess.run([sys.executable, os.path.join(SIMT, "selftest", "selftest.py")], capture_output=True, text=True, timeout=500)
+    assert r.returncode == 0 and "simt selftest ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
