@@ -560,6 +560,9 @@ static const unsigned long long kSig6L4 = 1ull | 1ull << 3 | 1ull << 6 | 1ull <<
 static const unsigned long long kSig6L5 = 1ull | 1ull << 3 | 1ull << 6 | 1ull << 9 | 1ull << 12 | 1ull << 15 | 1ull << 18 |
                                           2ull << 21 | 2ull << 24 | 3ull << 27 | 4ull << 30 | 3ull << 33;
 
+// BASELINE configs[3]: the 17-component chain (8 ISSE levels, one 16-input MIX)
+static const unsigned long long kSig6C17 = 1ull | 1ull << 3 | 1ull << 6 | 1ull << 9 | 1ull << 12 | 1ull << 15 | 1ull << 18 | 1ull << 21 | 2ull << 24;
+
 template <unsigned long long SIG, int V>
 static cudaError_t launch6(const ZKernelArgs* a, int ctas, int threads, size_t smem, int pw_bytes, int teams, cudaStream_t st) {
   static bool attr_set = false;
@@ -579,6 +582,7 @@ template <int V>
 static cudaError_t launch6v(const ZKernelArgs* a, int ctas, int th, size_t smem, int pw_bytes, int teams, unsigned long long sig, cudaStream_t st) {
   if (sig == kSig6L5) return launch6<kSig6L5, V>(a, ctas, th, smem, pw_bytes, teams, st);
   if (sig == kSig6L4) return launch6<kSig6L4, V>(a, ctas, th, smem, pw_bytes, teams, st);
+  if (sig == kSig6C17) return launch6<kSig6C17, V>(a, ctas, th, smem, pw_bytes, teams, st);
   return launch6<0ull, V>(a, ctas, th, smem, pw_bytes, teams, st);
 }
 
