@@ -5,8 +5,9 @@ Contract (see the task statement): one JSON line on rank 0.
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # libzpaq 7.15 on the host cores
+  python bench.py --config m4_256 | chain17_512            # BASELINE configs[1] / configs[3] (not the headline line)
 
-Workload (BASELINE.json configs[2]): 1 GiB of synthetic 1 MiB-class blocks
+Workload (BASELINE.json configs[2], the default): 1 GiB of synthetic 1 MiB-class blocks
 (payload 1 044 480 B = 2^20 - 4096, what `zpaq -method 50` produces) coded with
 -method 5, per GPU (weak scaling: blocks are independent, every rank codes its
 own 1 GiB, no data-path collective).  A "step" is one full compress pass plus
@@ -17,6 +18,12 @@ one full decompress pass over that batch through the public C ABI
               in HBM when the kernels start), from CUDA events on the library's
               stream (zpq_last_timing),
   * `roofline` = algorithmic HBM bytes of the coding kernels / their duration.
+
+Run time: the whole run is kept inside ZPQ_BENCH_BUDGET_S (default 600 s) of wall clock.  The first warm-up step is a
+full-size step (it allocates the workspace and brings the clocks up); the remaining W-1 warm-up steps run the same two
+calls on the first 1/8 of the batch (the kernels keep no state between calls: every call re-initialises its tables).
+If K timed steps would not fit the budget the run stops early and the line reports the steps actually timed
+(`steps`) next to `steps_requested` -- a flagged line instead of a killed process.
 """
 import argparse
 import ctypes as C
@@ -28,15 +35,29 @@ import sys
 import threading
 import time
 
+T_START = time.time()
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 BLOCK = (1 << 20) - 4096
-KIND = 1            # "mixed" generator
 SEED = 777
-METHOD = "5"
+CHAIN17 = "x0,0ci1,1,1,1,1,1,1,1c256c8,0,255c16,0,255,255aw1c0,0,255,1001,255c0,1010,255m16,24"
+# name -> (method string for this library, method string for libzpaq::compressBlock, total bytes per GPU, generator, label)
+CONFIGS = {
+    "m5_1g": ("5", "50", 1 << 30, 1, "BASELINE configs[2]: -method 5 (23-component makeConfig CM chain), 1 GiB of 1 MiB-class blocks per GPU, 'mixed' LCG text"),
+    "m4_256": ("4", "40", 256 * BLOCK, 0, "BASELINE configs[1]: -method 4 (8-component ICM/ISSE chain + MATCH + MIX), 256 x 1 MiB-class 'text' blocks"),
+    "chain17_512": (CHAIN17, CHAIN17, 1 << 29, 1, "BASELINE configs[3]: custom 17-component chain (8-deep ISSE chain, 16-input MIX with 2^16 weight sets), 512 MiB of 1 MiB-class 'mixed' blocks"),
+}
+KIND_NAME = {0: "text", 1: "mixed", 2: "random"}
 METRIC = "compress+decompress MB/s (-method 5), 1 GiB of 1 MiB blocks per GPU, bit-exact vs CPU ref"
+BUDGET_S = float(os.environ.get("ZPQ_BENCH_BUDGET_S", "600"))
+
+
+def metric_name(cfg):
+    if cfg == "m5_1g":
+        return METRIC
+    return "compress+decompress MB/s (%s), bit-exact vs CPU ref" % cfg
 
 
 def alg_bytes_per_input_byte(hdr, block_bytes):
@@ -139,11 +160,84 @@ class ClockSampler(threading.Thread):
                 "samples": len(s), "source": self.how}
 
 
-def host_threads():
+def host_info():
+    """What the host side of this lease really is: affinity, cgroup CPU quota, CPU model (a throttled lease and a whole host
+    both show 128 in sched_getaffinity)."""
     try:
-        return len(os.sched_getaffinity(0))
+        aff = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        aff = os.cpu_count() or 1
+    quota = None
+    raw = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            raw = open(path).read().strip()
+            if path.endswith("cpu.max"):
+                q, per = raw.split()
+                if q != "max":
+                    quota = float(q) / float(per)
+            else:
+                q = float(raw)
+                per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    quota = q / per
+            break
+        except Exception:
+            continue
+    model = None
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    eff = aff if quota is None else max(1, min(aff, int(quota + 0.999)))
+    par = measured_parallelism(aff)
+    if par is not None:
+        eff = max(1, min(eff, int(par + 0.75)))
+    return {"affinity": aff, "nproc": os.cpu_count(), "cgroup_cpu_max": raw, "cgroup_quota_cpus": quota, "cpu_model": model,
+            "measured_parallelism": par, "threads_used": eff}
+
+
+_PAR = {}
+
+
+def measured_parallelism(nthreads):
+    """How many host cores this process really gets: a pure-compute loop (the block generator, 4 MB per thread) on
+    `nthreads` threads against the same loop on one thread.  A lease with a CPU quota or shared cores shows the quota here
+    even when the cgroup files are not visible.  ~0.1 s, cached."""
+    if nthreads in _PAR:
+        return _PAR[nthreads]
+    try:
+        import oraclepy as O
+        Lo = O.lib()
+        n = 2 << 20
+        bufs = [C.create_string_buffer(n) for _ in range(nthreads)]
+
+        def work(i):
+            for rep in range(6):
+                Lo.zpqo_gen_block(2, 12345 + i + rep, bufs[i], n)
+
+        def timed(k):
+            th = [threading.Thread(target=work, args=(i,)) for i in range(k)]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            return time.perf_counter() - t0
+        timed(1)
+        t1 = min(timed(1), timed(1))
+        tn = min(timed(nthreads), timed(nthreads))
+        _PAR[nthreads] = nthreads * t1 / tn
+    except Exception:
+        _PAR[nthreads] = None
+    return _PAR[nthreads]
+
+
+def host_threads():
+    return host_info()["threads_used"]
 
 
 def reference_lib():
@@ -151,7 +245,7 @@ def reference_lib():
     if not refpy.available():
         return None
     try:
-        L = refpy.lib()
+        refpy.lib()
         refpy.compress_block(b"probe" * 100, "4")      # the x86 JIT needs RWX pages; fall back to the interpreter build
         return refpy
     except Exception:
@@ -160,53 +254,62 @@ def reference_lib():
         return refpy
 
 
-def cpu_reference_sample(threads, blocks_per_thread=1, block_bytes=BLOCK):
-    """libzpaq 7.15 compress+decompress of `threads*blocks_per_thread` blocks, one block per thread at a time.
-    `block_bytes` < BLOCK shortens every block (same generator, same method) to bound the sample's run time."""
+def cpu_reference_sample(cfg, threads, nblk=None):
+    """libzpaq 7.15 compress+decompress of `nblk` FULL-SIZE blocks (default: one per thread) of the configuration's
+    workload, one block per thread at a time as zpaq.cpp:1918 does; every block is compressed once and the archives just
+    written are decompressed (one pass, ref_bench_rt)."""
+    method, ref_method, _, kind, _ = CONFIGS[cfg]
     refpy = reference_lib()
-    nblk = max(1, threads * blocks_per_thread)
+    nblk = max(1, nblk or threads)
+    info = host_info()
     if refpy is not None:
-        t_c, _ = refpy.bench(METHOD + "0", nblk, block_bytes, KIND, SEED, threads, 0)
-        t_all, _ = refpy.bench(METHOD + "0", nblk, block_bytes, KIND, SEED, threads, 1)
-        t_d = t_all  # mode 1 times the decompress phase only (archives prepared untimed)
-        kind = "reference"
+        t_c, t_d = refpy.bench_rt(ref_method, nblk, BLOCK, kind, SEED, threads)
+        how = "reference"
     else:
         import oraclepy as O
         import zpaq_b200 as Z
-        t0 = time.time()
-        data = O.gen_block(KIND, SEED, BLOCK)
-        hdr = Z.model_from_method(METHOD, data)
+        data = O.gen_block(kind, SEED, BLOCK)
+        hdr = Z.model_from_method(method, data)
         t0 = time.time(); coded = O.encode(hdr, b"\0" + data); t_c = time.time() - t0
         t0 = time.time(); O.decode(hdr, coded + b"\0\0\0\0", BLOCK + 1); t_d = time.time() - t0
-        nblk, threads, kind, block_bytes = 1, 1, "port", BLOCK
-    mb = nblk * block_bytes / 1e6
-    return {"value": mb / (t_c + t_d), "unit": "MB/s", "cores": threads, "kind": kind,
-            "compress_MBps": mb / t_c, "decompress_MBps": mb / t_d,
-            "sample": "%d blocks x %d B, method %s, '%s' data, %d host threads (one block per thread), compress then decompress"
-                      % (nblk, block_bytes, METHOD, "mixed", threads)}
+        nblk, threads, how = 1, 1, "port"
+    mb = nblk * BLOCK / 1e6
+    return {"value": mb / (t_c + t_d), "unit": "MB/s", "cores": threads, "kind": how,
+            "compress_MBps": mb / t_c, "decompress_MBps": mb / t_d, "seconds": t_c + t_d, "host": info,
+            "sample": "%d blocks x %d B (full size), %s, '%s' data, %d host threads (one block per thread at a time), compress then decompress"
+                      % (nblk, BLOCK, "-method " + method if len(method) < 3 else "custom chain", KIND_NAME[kind], threads)}
 
 
 def run_reference(args, rank):
+    """Reference arm: the unmodified libzpaq on the box's host cores, same config / metric / unit.  A step = one full-size
+    block per usable host thread, compressed and decompressed; the CPU coder keeps no state between blocks (every block
+    starts from freshly initialised tables), so the W warm-up steps are one small untimed pass."""
     if rank != 0:
         return
+    cfg = args.config
+    method, ref_method, total, kind, label = CONFIGS[cfg]
     threads = host_threads()
-    # The CPU coder has no warm state (every block starts from freshly initialised tables), so the W warm-up steps are not
-    # run.  A step = one block per host thread, compressed then decompressed; one full-size step is about a minute of CPU
-    # time, so with more than three steps every block is shortened in proportion (same generator, same method): the whole
-    # arm stays within a few minutes and MB/s per thread barely depends on the block length.
-    block_bytes = BLOCK if args.steps <= 3 else max(1 << 16, (BLOCK * 3 // args.steps) & ~4095)
-    best = []
+    if args.warmup > 0:
+        cpu_reference_sample(cfg, min(threads, 4), 4)
     t_begin = time.time()
+    samples = []
     for i in range(args.steps):
-        best.append(cpu_reference_sample(threads, block_bytes=block_bytes))
+        # bounded: stop when the next step would leave the budget (a step is ~10-30 s of wall clock)
+        if samples and (time.time() - T_START) + 1.3 * samples[-1]["seconds"] > BUDGET_S * 0.6:
+            break
+        samples.append(cpu_reference_sample(cfg, threads))
     dt = time.time() - t_begin
-    v = sum(b["value"] for b in best) / len(best)
-    cb = dict(best[-1]); cb["value"] = v
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "-method 5 (makeConfig level-5 CM chain), 1 MiB-class blocks, bounded sample per step (see cpu_baseline.sample)",
-                       "block_bytes": BLOCK, "method": METHOD},
+    tot_mb = sum(s["seconds"] * s["value"] for s in samples)
+    tot_s = sum(s["seconds"] for s in samples)
+    v = tot_mb / tot_s
+    cb = dict(samples[-1]); cb["value"] = v
+    cb["compress_MBps"] = tot_mb / sum(s["seconds"] * s["value"] / s["compress_MBps"] for s in samples)
+    cb["decompress_MBps"] = tot_mb / sum(s["seconds"] * s["value"] / s["decompress_MBps"] for s in samples)
+    line = {"impl": "reference", "metric": metric_name(cfg), "value": v, "unit": "MB/s", "n_gpus": args.gpus, "steps": len(samples),
+            "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(1, len(samples)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": label + "; reference arm: bounded sample per step = one full-size block per usable host thread (see cpu_baseline.sample)",
+                       "block_bytes": BLOCK, "blocks_per_step": threads, "method": method},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -215,10 +318,11 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--blocks", type=int, default=0, help="blocks per GPU (default: 1 GiB worth = 1029)")
+    ap.add_argument("--config", default="m5_1g", choices=sorted(CONFIGS))
+    ap.add_argument("--blocks", type=int, default=0, help="blocks per GPU (default: the configuration's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -243,10 +347,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    total = 1 << 30
+    cfg = args.config
+    METHOD, ref_method, total, KIND, label = CONFIGS[cfg]
     nblk = args.blocks or (total + BLOCK - 1) // BLOCK
     sizes = [BLOCK] * nblk
-    if not args.blocks:
+    if not args.blocks and total % BLOCK:
         sizes[-1] = total - BLOCK * (nblk - 1)
     nbytes = sum(sizes)
 
@@ -256,11 +361,19 @@ def main():
     base = host_in.data_ptr()
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     Lo = O.lib()
-    for i in range(nblk):
-        Lo.zpqo_gen_block(KIND, (SEED + rank * 100003 + i) & 0xFFFFFFFF, C.c_void_p(base + int(offs[i])), sizes[i])
+
+    def gen(lo, hi):
+        for i in range(lo, hi):
+            Lo.zpqo_gen_block(KIND, (SEED + rank * 100003 + i) & 0xFFFFFFFF, C.c_void_p(base + int(offs[i])), sizes[i])
+    gth = [threading.Thread(target=gen, args=(k * nblk // 8, (k + 1) * nblk // 8)) for k in range(8)]
+    for t in gth:
+        t.start()
+    for t in gth:
+        t.join()
     bound = int(Z.lib().zpq_compress_bound(BLOCK)) + 4096
     host_arc = torch.empty(nblk * bound, dtype=torch.uint8, pin_memory=True)
     host_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    arc_cat = torch.empty(nblk * bound, dtype=torch.uint8, pin_memory=True)
     gen_s = time.time() - t0
 
     ctx = Z.Context(local_rank)
@@ -271,12 +384,12 @@ def main():
     ocap = (C.c_uint64 * nblk)(*([bound] * nblk))
     olen = (C.c_uint64 * nblk)()
     stat = (C.c_int32 * nblk)()
-    arc_cat = torch.empty(nblk * bound, dtype=torch.uint8, pin_memory=True)
 
-    def one_step():
-        """compress every block, concatenate the archive, decompress it; returns timing dict."""
+    def one_step(nb=nblk):
+        """compress the first `nb` blocks, concatenate the archive, decompress it; returns timing dict."""
+        nby = int(offs[nb])
         t0 = time.perf_counter()
-        rc = L.zpq_compress_blocks(ctx._h, nblk, METHOD.encode(), dptr, lens, None, None, 1, optr, ocap, olen, stat)
+        rc = L.zpq_compress_blocks(ctx._h, nb, METHOD.encode(), dptr, lens, None, None, 1, optr, ocap, olen, stat)
         t1 = time.perf_counter()
         if rc:
             raise SystemExit("zpq_compress_blocks failed: %d %s" % (rc, ctx.last_error()))
@@ -284,23 +397,23 @@ def main():
         # archive = blocks back to back (what zpaq's writer thread appends, zpaq.cpp:1968)
         pos = 0
         src = host_arc.numpy(); dst = arc_cat.numpy()
-        for i in range(nblk):
+        for i in range(nb):
             n = olen[i]
             dst[pos:pos + n] = src[i * bound:i * bound + n]
             pos += n
-        n_out = C.c_uint64(0); nb = C.c_int(0)
+        n_out = C.c_uint64(0); nbk = C.c_int(0)
         t2 = time.perf_counter()
-        rc = L.zpq_decompress_archive(ctx._h, C.c_void_p(arc_cat.data_ptr()), pos, C.c_void_p(host_out.data_ptr()), nbytes,
-                                      C.byref(n_out), C.byref(nb), 1)
+        rc = L.zpq_decompress_archive(ctx._h, C.c_void_p(arc_cat.data_ptr()), pos, C.c_void_p(host_out.data_ptr()), nby,
+                                      C.byref(n_out), C.byref(nbk), 1)
         t3 = time.perf_counter()
         if rc:
             raise SystemExit("zpq_decompress_archive failed: %d %s" % (rc, ctx.last_error()))
         td = ctx.timing()
-        if n_out.value != nbytes or nb.value != nblk:
+        if n_out.value != nby or nbk.value != nb:
             raise SystemExit("round trip size mismatch")
         return {"wall_c": t1 - t0, "wall_d": t3 - t2, "dev_c": (tc["init_ms"] + tc["code_ms"]) / 1e3,
                 "dev_d": (td["init_ms"] + td["code_ms"]) / 1e3, "code_c": tc["code_ms"] / 1e3, "code_d": td["code_ms"] / 1e3,
-                "arc_bytes": pos}
+                "arc_bytes": pos, "wall": t3 - t0}
 
     def barrier():
         torch.cuda.synchronize()
@@ -308,11 +421,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        r = one_step()
-    # round trip must be exact
-    if not bool(torch.equal(host_in, host_out)) and args.warmup > 0:
-        raise SystemExit("round trip mismatch")
+    def agree(flag):
+        """the same decision on every rank (max over ranks)"""
+        if dist is None:
+            return flag
+        t = torch.tensor([1.0 if flag else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item() > 0)
+
+    # ---- warm-up: one full-size step (workspace allocation, clocks), then W-1 steps on the first 1/8 of the batch ----
+    reserve_s = 25.0 + (0.0 if args.no_cpu_baseline else 45.0)       # CPU baseline, bit-exact sample, teardown
+    nb_small = max(1, min(nblk, (nblk + 7) // 8))
+    step_est = None
+    for w in range(args.warmup):
+        full = (w == 0)
+        r = one_step(nblk if full else nb_small)
+        if full:
+            step_est = r["wall"]
+            if not bool(torch.equal(host_in, host_out)):
+                raise SystemExit("round trip mismatch")
+    warm_s = time.time() - T_START
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -320,10 +448,17 @@ def main():
     barrier()
     acc = {"wall_c": 0.0, "wall_d": 0.0, "dev_c": 0.0, "dev_d": 0.0, "code_c": 0.0, "code_d": 0.0}
     t_begin = time.perf_counter()
-    for _ in range(args.steps):
+    done = 0
+    for k in range(args.steps):
+        if step_est is not None and done >= 1:
+            over = (time.time() - T_START) + 1.1 * step_est + reserve_s > BUDGET_S
+            if agree(over):
+                break
         r = one_step()
-        for k in acc:
-            acc[k] += r[k]
+        step_est = r["wall"]
+        done += 1
+        for key in acc:
+            acc[key] += r[key]
     barrier()
     wall = time.perf_counter() - t_begin
     launches = ctx.launch_count() - launches0
@@ -337,12 +472,13 @@ def main():
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     wall_c, wall_d, dev_c, dev_d, code_c, code_d, wall = [float(x) for x in times.cpu()]
-    tot_bytes = nbytes * world * args.steps
+    tot_bytes = nbytes * world * done
     mb = tot_bytes / 1e6
 
     if rank == 0:
         hdr = Z.model_from_method(METHOD, bytes(host_in.numpy()[:sizes[0]]))
         balg = alg_bytes_per_input_byte(hdr, BLOCK)
+        arena_bytes = Z.model_bytes(hdr)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -350,47 +486,63 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # dominant kernel = the coding kernels (one compress + one decompress launch per step, per rank)
-        per_rank_alg = nbytes * args.steps * balg * 2          # both directions touch the same tables
+        # dominant kernels = the coding kernels of the two directions (per rank)
+        per_rank_alg = nbytes * done * balg * 2          # both directions touch the same tables
         achieved = per_rank_alg / (code_c + code_d) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        except Exception:
+            pass
         # bit-exactness against the CPU reference on a bounded sample, and the CPU baseline itself
         cpu = None
         bit_exact = None
         if not args.no_cpu_baseline:
-            cpu = cpu_reference_sample(host_threads())
             refpy = reference_lib()
             if refpy is not None:
                 k = min(4, nblk)
-                ok = True
-                for i in range(k):
-                    want = refpy.compress_block(bytes(host_in.numpy()[offs[i]:offs[i + 1]]), METHOD)
-                    got = bytes(host_arc.numpy()[i * bound:i * bound + olen[i]])
-                    ok = ok and (want == got)
-                bit_exact = ok
+                want = [None] * k
+
+                def ref_one(i):
+                    want[i] = refpy.compress_block(bytes(host_in.numpy()[offs[i]:offs[i + 1]]), ref_method)
+                th = [threading.Thread(target=ref_one, args=(i,)) for i in range(k)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                bit_exact = all(want[i] == bytes(host_arc.numpy()[i * bound:i * bound + olen[i]]) for i in range(k))
+            left = BUDGET_S - (time.time() - T_START) - 15.0
+            ht = host_threads()
+            # one full-size block per usable host thread is ~10-30 s; with little budget left, fewer blocks
+            cpu = cpu_reference_sample(cfg, ht, ht if left > 40 else max(1, ht // 4))
         line = {
-            "metric": METRIC, "value": mb / (dev_c + dev_d), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: -method 5 (23-component makeConfig CM chain), %d blocks x %d B per GPU "
-                                   "(1 GiB), 'mixed' LCG text, seeds %d+rank*100003+block" % (nblk, BLOCK, SEED),
+            "metric": metric_name(cfg), "value": mb / (dev_c + dev_d), "unit": "MB/s", "n_gpus": world, "steps": done,
+            "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, done), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "%s; %d blocks x %d B per GPU, seeds %d+rank*100003+block" % (label, nblk, BLOCK, SEED),
                        "blocks_per_gpu": nblk, "block_bytes": BLOCK, "method": METHOD, "parallelism": "block-shard x%d, no data-path collective" % world,
-                       "cache": "each step touches %.0f GB of model tables per GPU (>> 126 MB L2); tables are re-initialised every launch"
-                                % (nblk * 88.07e6 / 1e9)},
+                       "cache": "inputs larger than L2: each step touches %.1f GB of model tables per GPU (>> 126 MB L2); tables are re-initialised every launch"
+                                % (nblk * arena_bytes / 1e9),
+                       "warmup_detail": "step 1 full size, steps 2..W on the first %d blocks" % nb_small,
+                       "budget_s": BUDGET_S, "truncated": done < args.steps},
             "compress_MBps": mb / dev_c, "decompress_MBps": mb / dev_d,
             "e2e": {"value": mb / (wall_c + wall_d), "unit": "MB/s", "compress_MBps": mb / wall_c, "decompress_MBps": mb / wall_d,
                     "h2d_bytes_per_step": int(nbytes + r["arc_bytes"]), "d2h_bytes_per_step": int(r["arc_bytes"] + nbytes)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "alg_bytes_per_input_byte": balg, "kernel": "zpq_wave_kernel (encode, 525 launches per step) + zpq_dec_kernel6 (decode)",
-                         "kernel_variants": {"ZPQ_WAVE_VARIANT": os.environ.get("ZPQ_WAVE_VARIANT", "25 (default)"),
-                                             "ZPQ_DEC_VARIANT": os.environ.get("ZPQ_DEC_VARIANT", "31 (default)")},
+                         "traffic": traffic, "peak_source": peak_src,
+                         "alg_bytes_per_input_byte": balg,
+                         "encode": {"achieved": nbytes * done * balg / code_c / 1e9, "frac": nbytes * done * balg / code_c / 1e9 / peak},
+                         "decode": {"achieved": nbytes * done * balg / code_d / 1e9, "frac": nbytes * done * balg / code_d / 1e9 / peak},
+                         "kernel": "encode + decode coding kernels (see DESIGN.md section 3)",
+                         "kernel_variants": {k: v for k, v in os.environ.items() if k.startswith("ZPQ_") and k != "ZPQ_BENCH_BUDGET_S"},
                          "note": "latency/issue bound, not bandwidth bound (see profiles/ and DESIGN.md section 6)"},
             "cpu_baseline": cpu, "bit_exact_vs_reference": bit_exact, "clocks": clocks,
-            "archive_ratio": r["arc_bytes"] / nbytes, "setup_s": gen_s,
+            "archive_ratio": r["arc_bytes"] / nbytes, "setup_s": gen_s, "warmup_s": warm_s, "total_s": time.time() - T_START,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

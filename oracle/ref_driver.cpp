@@ -31,6 +31,7 @@ void error(const char* msg) { throw std::runtime_error(msg); }
 }  // namespace libzpaq
 
 namespace {
+double* g_secs2 = nullptr;   // ref_bench_rt: where ref_bench leaves both phase times
 std::string g_err;  // last error (callers are single threaded; bench workers only write on failure)
 
 struct MemReader : public libzpaq::Reader {
@@ -199,11 +200,21 @@ double ref_bench(const char* method, int nblocks, long long blocksize, int kind,
       return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     };
     double secs = run(false);
-    if (mode == 1 && !failed) secs = run(true);
+    if (g_secs2) { g_secs2[0] = secs; g_secs2[1] = 0; }
+    if ((mode == 1 || mode == 2) && !failed) { secs = run(true); if (g_secs2) g_secs2[1] = secs; }
     if (failed) { if (failed == 2) g_err = "round trip mismatch"; return -1.0; }
     if (total_out) *total_out = total;
     return secs;
   } catch (std::exception& e) { g_err = e.what(); return -1.0; }
+}
+
+// One pass that times both directions: secs2[0] = compress, secs2[1] = decompress of the archives just written
+// (bench.py's bounded CPU sample: every block is compressed once, not twice).
+int ref_bench_rt(const char* method, int nblocks, long long blocksize, int kind, unsigned seed, int threads, double* secs2) {
+  g_secs2 = secs2;
+  const double s = ref_bench(method, nblocks, blocksize, kind, seed, threads, 2, nullptr);
+  g_secs2 = nullptr;
+  return s < 0 ? -1 : 0;
 }
 
 // Static tables of the reference after Predictor::init() (libzpaq.cpp:1731-1750)

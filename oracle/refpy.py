@@ -36,6 +36,8 @@ def lib(nojit=False):
         L.ref_bench.restype = C.c_double
         L.ref_bench.argtypes = [C.c_char_p, C.c_int, C.c_longlong, C.c_int, C.c_uint, C.c_int, C.c_int,
                                 C.POINTER(C.c_longlong)]
+        L.ref_bench_rt.restype = C.c_int
+        L.ref_bench_rt.argtypes = [C.c_char_p, C.c_int, C.c_longlong, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_double)]
         L.ref_gen_block.restype = None
         L.ref_gen_block.argtypes = [C.c_int, C.c_uint, C.c_char_p, C.c_longlong]
         _lib = L
@@ -103,3 +105,11 @@ def bench(method, nblocks, blocksize, kind, seed, threads, mode):
     if s < 0:
         raise _err()
     return s, tot.value
+
+
+def bench_rt(method, nblocks, blocksize, kind, seed, threads):
+    """(compress seconds, decompress seconds) of one pass over `nblocks` blocks on `threads` host threads."""
+    t = (C.c_double * 2)()
+    if lib().ref_bench_rt(method.encode(), nblocks, blocksize, kind, seed, threads, t) < 0:
+        raise _err()
+    return t[0], t[1]

@@ -7,6 +7,7 @@ The translation is textual and touches only what g++ cannot parse:
   kernel<<<grid, block, smem, stream>>>(args);    ->  simt_launch(dim3(grid), dim3(block), smem, [&]() { kernel(args); });
   extern __shared__ ... unsigned char smem[];     ->  unsigned char* smem = simt_dyn_smem();
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory")   ->  simt_named_barrier(id, count)
+  asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory") ->  simt_named_arrive(id, count)
   asm volatile("prefetch.global.L1|L2 [%0];" :: "l"(p))                ->  (void)(p)
   while (cond) { }      (spin on a volatile shared word)               ->  while (cond) { simt_spin(); }
   for (...; cond;) { if (++spin > SPIN_CAP) ... }   (capped spin)      ->  ... { simt_spin(); if (++spin > SPIN_CAP) ... }
@@ -21,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "zpaq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
-CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels3.cu", "zpq_kernels4.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_abi.cu"]
+CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels3.cu", "zpq_kernels4.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_abi.cu"]
 CPP = ["zpq_model.cpp", "zpq_method.cpp", "zpq_frame.cpp", "zpq_hcomp.cpp"]
 
 
@@ -53,6 +54,8 @@ def translate(text, name):
     text, n_launch = LAUNCH.subn(launch, text)
     text, n_smem = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];", r"unsigned char* \1 = simt_dyn_smem();", text)
     text, n_bar = re.subn(r'asm volatile\("bar\.sync %0, %1;"\s*::\s*"r"\((.*?)\),\s*"r"\((\d+)\)\s*:\s*"memory"\)', r"simt_named_barrier(\1, \2)", text)
+    text, n_arr = re.subn(r'asm volatile\("bar\.arrive %0, %1;"\s*::\s*"r"\((.*?)\),\s*"r"\((\d+)\)\s*:\s*"memory"\)', r"simt_named_arrive(\1, \2)", text)
+    n_bar += n_arr
     text, n_pf = re.subn(r'asm volatile\("prefetch\.global\.L[12] \[%0\];"\s*::\s*"l"\((\w+)\)\)', r"(void)(\1)", text)
     text, n_spin = re.subn(r"(while \(.*\)) \{ \}", r"\1 { simt_spin(); }", text)
     text, n_spin2 = re.subn(r"\{ if \(\+\+(spin_?) > SPIN_CAP\)", r"{ simt_spin(); if (++\1 > SPIN_CAP)", text)     # capped spin loops

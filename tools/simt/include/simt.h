@@ -58,6 +58,7 @@ unsigned char* simt_dyn_smem();
 const uint64_t* simt_warp_exchange(unsigned mask, uint64_t v, unsigned* took_part);
 void simt_syncthreads();
 void simt_named_barrier(int id, int count);
+void simt_named_arrive(int id, int count);
 void simt_spin();
 int simt_lane();
 void simt_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);

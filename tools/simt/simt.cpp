@@ -277,6 +277,13 @@ void simt_named_barrier(int id, int count) {
   bar_wait(f, w, &b.gen, g);
 }
 
+// bar.arrive: counts the thread in, never waits (the producer side of a producer / consumer barrier)
+void simt_named_arrive(int id, int count) {
+  Fiber* f = t_self; Cta* c = f->cta;
+  NamedBar& b = c->named[id & 15];
+  if (++b.arrived >= count) { b.arrived = 0; ++b.gen; }
+}
+
 void simt_spin() {
   // one fruitless look at the flag: let the warp's other lanes run (one of them may be the flag's writer in another
   // role, or may still have to publish something), then the other warps

@@ -39,7 +39,7 @@ EXPORTS = ["zpq_abi_version", "zpq_create", "zpq_destroy", "zpq_strerror", "zpq_
            "zpq_set_workspace", "zpq_set_stream", "zpq_model_bytes", "zpq_model_from_method",
            "zpq_encode_blocks", "zpq_decode_blocks", "zpq_encode_blocks_dev", "zpq_decode_blocks_dev",
            "zpq_last_timing", "zpq_launch_count", "zpq_compress_blocks", "zpq_decompress_archive",
-           "zpq_compress_bound", "zpq_postprocess_block", "zpq_model_describe"]
+           "zpq_compress_bound", "zpq_postprocess_block", "zpq_model_describe", "zpq_last_tiers"]
 
 _lib = None
 
@@ -69,6 +69,7 @@ def lib():
             f.argtypes = [vp, i32, C.POINTER(Job)]
         L.zpq_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
         L.zpq_launch_count.argtypes = [vp]
+        L.zpq_last_tiers.argtypes = [vp, C.POINTER(C.c_uint32)]
         L.zpq_launch_count.restype = u64
         L.zpq_compress_blocks.argtypes = [vp, i32, C.c_char_p, vp, vp, vp, vp, i32, vp, vp, vp, vp]
         L.zpq_decompress_archive.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(i32), i32]
@@ -157,6 +158,12 @@ class Context:
         ms = (C.c_float * 3)()
         lib().zpq_last_timing(self._h, ms)
         return {"init_ms": ms[0], "code_ms": ms[1], "call_ms": ms[2]}
+
+    def tiers(self):
+        """Blocks of the last batch per kernel tier (zpq_last_tiers): wave encoder, dec7, dec6, fast, generic, wide generic."""
+        t = (C.c_uint32 * 6)()
+        lib().zpq_last_tiers(self._h, t)
+        return dict(zip(("wave_enc", "dec7", "dec6", "fast", "generic", "wide"), [int(x) for x in t]))
 
     def launch_count(self):
         return int(lib().zpq_launch_count(self._h))

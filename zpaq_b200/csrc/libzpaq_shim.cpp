@@ -16,8 +16,8 @@
 //   * Decompresser::decompress(n): the first call of a segment pulls the segment's coded bytes from the
 //     Reader (through Decoder::get, so buffered() keeps its meaning), decodes them with zpq_decode_blocks
 //     and then serves n bytes per call through the object's own PostProcessor (PASS and PCOMP alike:
-//     post-processing is not part of the hot path and stays the reference's code).  Blocks whose model
-//     the GPU library does not take (stored blocks, n > 32 components) keep the reference's CPU decoder.
+//     post-processing is not part of the hot path and stays the reference's code).  Stored blocks (no model)
+//     keep the reference's CPU code; a MODELLED block the kernels cannot take raises error(), never a CPU decode.
 #include "libzpaq.h"
 #include "../../include/zpq.h"
 #include <condition_variable>
@@ -145,17 +145,25 @@ struct Batcher {
 
 Batcher& batcher() { static Batcher* b = new Batcher(); return *b; }
 
+// does the CUDA library code blocks of this (valid, modelled) header?
+bool gpu_takes(const uint8_t* hdr, int hlen) {
+  uint32_t info[8];
+  return zpq_model_describe(hdr, hlen, info) == ZPQ_OK;
+}
+
 }  // namespace
 
 void compressBlock(StringBuffer* in, Writer* out, const char* method, const char* filename, const char* comment, bool dosha1) {
   // which methods the GPU core takes is decided by the library itself (zpq_model_from_method)
   uint8_t hdr[70000]; int hlen = 0;
   const int probe = zpq_model_from_method(method, in->data(), in->size(), hdr, (int)sizeof(hdr), &hlen);
-  if (probe == ZPQ_E_METHOD || probe == ZPQ_E_UNSUPPORTED || (probe == ZPQ_OK && (hdr[6] == 0 || hdr[6] > 32))) {
+  if (probe == ZPQ_E_METHOD || probe == ZPQ_E_UNSUPPORTED || (probe == ZPQ_OK && hdr[6] == 0)) {
     SHIM_LOG("compressBlock %d bytes method %s -> reference CPU code (not a context-model method)", (int)in->size(), method);
     compressBlock_cpu(in, out, method, filename, comment, dosha1);     // LZ77 / BWT / stored: not on the hot path
     return;
   }
+  if (probe == ZPQ_OK && !gpu_takes(hdr, hlen))       // a modelled block the kernels cannot take: say so, never code it on the CPU
+    error("context model not supported by the B200 core");
   if (probe != ZPQ_OK) error(zpq_strerror(probe));
   Req r;
   r.data = in->data(); r.len = in->size(); r.method = method; r.filename = filename; r.comment = comment; r.dosha1 = dosha1;
@@ -201,7 +209,12 @@ void compress(Reader* in, Writer* out, const char* method, const char* filename,
     for (size_t i = 0; i < bufs.size(); ++i) {
       uint8_t hdr[70000]; int hlen = 0;
       const int probe = zpq_model_from_method(method, bufs[i]->data(), bufs[i]->size(), hdr, (int)sizeof(hdr), &hlen);
-      if (probe == ZPQ_OK && hdr[6] > 0 && hdr[6] <= 32) {
+      if (probe == ZPQ_OK && hdr[6] > 0 && !gpu_takes(hdr, hlen)) {
+        for (size_t k = 0; k < i; ++k) if (on_gpu[k]) batcher().wait(&reqs[k]);
+        for (StringBuffer* sb : bufs) delete sb;
+        error("context model not supported by the B200 core");
+      }
+      if (probe == ZPQ_OK && hdr[6] > 0) {
         Req& r = reqs[i];
         r.data = bufs[i]->data(); r.len = bufs[i]->size(); r.method = method;
         r.filename = i == 0 ? filename : nullptr; r.comment = i == 0 ? comment : nullptr; r.dosha1 = dosha1;
@@ -252,6 +265,7 @@ struct DState {
   std::vector<uint8_t> plain;          // model output of the current segment (post-processor prefix included)
   uint64_t pos = 0;                    // bytes of `plain` already given to the post-processor
   bool have_plain = false;             // current segment decoded, its coded bytes consumed from the Reader
+  int marker = -2;                     // byte that followed the segment's zeros (253 / 254), read ahead; -2 = none
 };
 std::mutex g_dmu;
 std::map<const Decompresser*, DState*> g_dstate;
@@ -276,7 +290,11 @@ bool Decompresser::decompress(int n) {
       for (int i = 0; i < z.cend; ++i) S->hdr.push_back(z.header[i]);
       for (int i = z.hbegin; i < z.hend; ++i) S->hdr.push_back(z.header[i]);
       uint32_t info[8];
-      S->gpu = z.header[6] > 0 && zpq_model_describe(S->hdr.data(), (int)S->hdr.size(), info) == ZPQ_OK;
+      const int drc = z.header[6] > 0 ? zpq_model_describe(S->hdr.data(), (int)S->hdr.size(), info) : ZPQ_E_UNSUPPORTED;
+      S->gpu = drc == ZPQ_OK;
+      // a modelled block the kernels cannot take is an error, not a reason to decode it on the CPU (invalid headers
+      // still go to the reference's Predictor::init, which raises its own message)
+      if (z.header[6] > 0 && drc == ZPQ_E_UNSUPPORTED) error("context model not supported by the B200 core");
     }
     if (S->gpu) { pp.init(z.header[4], z.header[5]); decode_state = SEG; }     // dec.init() is the CPU model: not needed
     SHIM_LOG("Decompresser: block with %d components -> %s", z.header.isize() > 6 ? (int)z.header[6] : -1, S->gpu ? "GPU" : "reference CPU code");
@@ -284,16 +302,21 @@ bool Decompresser::decompress(int n) {
   if (!S->gpu) return zpq_ref_decompress(this, n);
 
   if (!S->have_plain) {
-    // the segment's coded bytes: everything up to and including the first run of four zero bytes
-    // (the coder never emits four zeros in a row, libzpaq.cpp:2414; Decoder::skip relies on the same rule)
+    // the segment's coded bytes: everything up to the end-of-segment marker.  The coder never emits four zeros in a
+    // row inside the data (libzpaq.cpp:2414), but the last bytes of the range flush may be zero, so the run that ends a
+    // segment is 4..7 zeros long: after four zeros keep reading zeros, the first other byte is the 253 / 254 marker
+    // (Decoder::skip: "might be more than 4", libzpaq.cpp:2165).  The GPU decoder wants all of them (it stops four
+    // bytes after the flush, at the end of its input).
     const uint64_t start = S->coded.size();
-    int zeros = 0;
+    int zeros = 0, c = 0;
     while (zeros < 4) {
-      const int c = dec.get();
+      c = dec.get();
       if (c < 0) error("unexpected end of file");
       S->coded.push_back((uint8_t)c);
       zeros = c == 0 ? zeros + 1 : 0;
     }
+    while ((c = dec.get()) == 0) S->coded.push_back(0);
+    S->marker = c;                                      // consumed here, parsed by readSegmentEnd below
     S->seg_len.push_back(S->coded.size() - start);
     // decode every segment of the block read so far (model and coder state carry over between segments,
     // libzpaq.cpp:2889); the output size is not known in advance: grow the buffer until it fits
@@ -391,11 +414,21 @@ void decompress(Reader* in, Writer* out) {
 void Decompresser::readSegmentEnd(char* sha1string) {
   DState* S = dstate(this);
   if (decode_state == FIRSTSEG) *S = DState();      // no decompress() in this block yet: whatever the table holds is an older object's
-  if (S->gpu && S->have_plain && state == DATA) {
-    // the segment's coded bytes (through their four zeros) are already consumed: nothing to skip, but as in the
-    // reference no further decompress() may follow in this block
+  if (S->gpu && S->marker != -2) {
+    // the segment's coded bytes, its zeros and the marker byte are already consumed (decompress above).  A segment
+    // left half way (state DATA) counts as skipped: as in the reference no further decompress() may follow in this block.
+    if (state == DATA) decode_state = SKIP;
     S->have_plain = false; S->plain.clear();
-    state = SEGEND; decode_state = SKIP;
+    int c = S->marker;
+    S->marker = -2;
+    state = FILENAME;
+    if (c == 254) { if (sha1string) sha1string[0] = 0; }
+    else if (c == 253) {
+      if (sha1string) sha1string[0] = 1;
+      for (int i = 1; i <= 20; ++i) { c = dec.get(); if (sha1string) sha1string[i] = (char)c; }
+    }
+    else error("missing end of segment marker");
+    return;
   }
   zpq_ref_readSegmentEnd(this, sha1string);
 }

@@ -64,11 +64,13 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   uint64_t launches = 0;
+  uint32_t tiers[6] = {0, 0, 0, 0, 0, 0};   // blocks of the last batch per kernel tier (zpq_last_tiers)
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
   int wave_variant = 25;       // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps, bit 4 nibble-unrolled ICM / ISSE loop
   int dec_variant = 31;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7 or 15) slot-scheduled hashes, bit 3 (15) MATCH in warp A, bit 4 (31) register-resident predictions in warp B
   bool wave_prof = false;      // ZPQ_WAVE_PROF=1: per-role warp cycles of the wavefront encoder to stderr
+  int dec_kernel = 7;           // ZPQ_DEC_KERNEL: 7 = critical-first two-warp decoder (zpq_kernels7.cu), 6 = round-1 two-warp decoder
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
 };
 
@@ -90,6 +92,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
   if (!ctx) return ZPQ_E_ARG;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   ctx->ms[0] = ctx->ms[1] = ctx->ms[2] = 0;
+  for (int t = 0; t < 6; ++t) ctx->tiers[t] = 0;
   const int nj = (int)jobs.size();
   if (nj == 0) return ZPQ_OK;
   const auto t_begin = std::chrono::steady_clock::now();
@@ -274,10 +277,11 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
         ZKernelArgs Ak = A;
         Ak.blocks = A.blocks + first; Ak.status = A.status + first; Ak.out_len = A.out_len + first;
         Ak.counter = A.counter + cls; Ak.nblk = cnt;
-        if (cls == 4) { CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch"); ++ctx->launches; }
+        if (cls == 4) { CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch"); ++ctx->launches; ctx->tiers[4] += (uint32_t)cnt; }
         else if (cls == 0) {
           // ---- wavefront encoder: groups of <= 32 blocks of one model, one launch per wave ----
           const int GS = ctx->wave_group;
+          ctx->tiers[0] += (uint32_t)cnt;
           std::vector<uint32_t> gfirst, gcount, bgroup(cnt), blane(cnt);
           int ncs = 2; uint64_t maxN = 0; uint32_t dmaxc = 0;
           for (int k = 0; k < cnt; ++k) {
@@ -356,15 +360,25 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
                 if (zpq_code2_signature(&models[jobs[wave[k]].model].fast) != sig) { sig = 0; break; }
               bool pair = decode && kv >= 5;
               for (int k = first; k < first + cnt && pair; ++k) pair = models[jobs[wave[k]].model].fast.pair_ok != 0;
-              if (pair) {
+              bool hp_all = true;
+              for (int k = first; k < first + cnt; ++k) if (!models[jobs[wave[k]].model].hplan.ok) { hp_all = false; break; }
+              if (pair && hp_all && ctx->dec_kernel >= 7 && zpq_dec7_takes(sig)) {
+                // two warps per block, critical-first ordering (zpq_kernels7.cu)
+                const uint64_t room7 = ZPQ_SMEM_MAX - (uint64_t)zpq_dec7_static_smem();
+                const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room7 / (pw + (uint64_t)zpq_dec7_ctrl_bytes())));
+                CK(zpq_launch_dec7(&Ak, cnt, ctx->sm_count, teams, (int)pw, sig, st), "zpq_dec_kernel7 launch");
+                ctx->tiers[1] += (uint32_t)cnt;
+              }
+              else if (pair) {
                 // two warps per block (zpq_kernels6.cu)
                 const uint64_t room6 = ZPQ_SMEM_MAX - (uint64_t)zpq_dec6_static_smem();
                 const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room6 / (pw + (uint64_t)zpq_dec6_ctrl_bytes())));
                 int dv = ctx->dec_variant;
                 if (dv & 4) for (int k = first; k < first + cnt; ++k) if (!models[jobs[wave[k]].model].hplan.ok) { dv &= 3; break; }   // 7 / 15 need the hash plan
                 CK(zpq_launch_dec6(&Ak, cnt, ctx->sm_count, teams, (int)pw, sig, dv, st), "zpq_dec_kernel6 launch");
+                ctx->tiers[2] += (uint32_t)cnt;
               }
-              else CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, sig, st), "zpq_code_kernel2 launch");
+              else { CK(zpq_launch_code2(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, warps, (int)pw, sig, st), "zpq_code_kernel2 launch"); ctx->tiers[3] += (uint32_t)cnt; }
             }
           }
           ++ctx->launches;
@@ -485,6 +499,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
   if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 31) ctx->wave_variant = v; }
   if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if ((v >= 0 && v <= 3) || v == 7 || v == 15 || v == 31) ctx->dec_variant = v; }
+  if (const char* dk = getenv("ZPQ_DEC_KERNEL")) { const int v = atoi(dk); if (v == 6 || v == 7) ctx->dec_kernel = v; }
   if (const char* wp = getenv("ZPQ_WAVE_PROF")) ctx->wave_prof = atoi(wp) != 0;
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
@@ -580,6 +595,12 @@ int zpq_last_timing(const zpq_ctx* ctx, float ms[3]) {
 }
 
 uint64_t zpq_launch_count(const zpq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zpq_last_tiers(const zpq_ctx* ctx, uint32_t tiers[6]) {
+  if (!ctx || !tiers) return ZPQ_E_ARG;
+  for (int t = 0; t < 6; ++t) tiers[t] = ctx->tiers[t];
+  return ZPQ_OK;
+}
 
 int zpq_postprocess_block(const uint8_t* hdr, int hlen, const uint8_t* model_out, const uint64_t* seg_len, int nseg,
                           uint8_t* out, uint64_t out_cap, uint64_t* out_len, uint64_t* seg_out) {
