@@ -12,30 +12,34 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-def _make_ctx(kernel):
+def _make_ctx(kernel, dec_kernel="7"):
     import zpaq_b200 as Z
-    old = os.environ.get("ZPQ_KERNEL")
+    old = {k: os.environ.get(k) for k in ("ZPQ_KERNEL", "ZPQ_DEC_KERNEL")}
     os.environ["ZPQ_KERNEL"] = kernel
+    os.environ["ZPQ_DEC_KERNEL"] = dec_kernel
     try:
         return Z.Context(0)   # raises if there is no GPU: GPU tests must not silently pass
     finally:
-        if old is None:
-            del os.environ["ZPQ_KERNEL"]
-        else:
-            os.environ["ZPQ_KERNEL"] = old
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
 
 
 @pytest.fixture(scope="session")
 def ctx():
-    """Production configuration: wavefront encoder + fast sequential decoder."""
+    """Production configuration: wavefront encoder + critical-first two-warp decoder."""
     c = _make_ctx("5")
     yield c
     c.close()
 
 
-@pytest.fixture(scope="session", params=["5", "4", "3", "2", "1"], ids=["wave", "team", "pipeline", "fast", "generic"])
+@pytest.fixture(scope="session", params=["5", "5/dec6", "2", "1"], ids=["production", "dec6", "fast", "generic"])
 def kctx(request):
-    """Every kernel tier: 5 = production (wavefront encoder), 4 = team encoder, 3 = one-warp pipeline encoder, 2 = fast sequential kernel for both directions, 1 = generic kernel."""
-    c = _make_ctx(request.param)
+    """Every kernel tier: 5 = production (wavefront encoder + critical-first two-warp decoder zpq_kernels7.cu), 5/dec6 = the
+    round-1 two-warp decoder (generic step lists fall back to it), 2 = one-warp kernel for both directions, 1 = generic kernel."""
+    k, _, d = request.param.partition("/dec")
+    c = _make_ctx(k, d or "7")
     yield c
     c.close()

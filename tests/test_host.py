@@ -117,3 +117,16 @@ def test_host_postprocessor_against_reference_archives(entry):
     else:
         mo = O.decode(hdr, coded + b"\0\0\0\0", 4 * len(want) + 70000)
     assert Z.postprocess_block(hdr, [mo]) == [want]
+
+
+def test_postprocessor_rejects_absurd_pcomp_sizes():
+    """ph / pm come straight from an untrusted header: values ZPAQL::init refuses (libzpaq.cpp:1009-1024, "H too big" /
+    "M too big") must come back as a status, not as a shift by 255 or a terabyte allocation."""
+    model_out = bytes([1, 1, 0, 56]) + b"abc"           # PROG, length 1, program = HALT, then data
+    for ph, pm in ((255, 0), (0, 200), (33, 33)):
+        hdr = bytes([8, 0, 9, 16, ph, pm, 0, 0, 56, 0])
+        with pytest.raises(Z.ZpqError) as e:
+            Z.postprocess_block(hdr, [model_out])
+        assert e.value.rc == -2
+    hdr = bytes([8, 0, 9, 16, 4, 8, 0, 0, 56, 0])
+    assert Z.postprocess_block(hdr, [model_out]) == [b""]   # a program that never OUTs produces nothing

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "zpaq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
-CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels3.cu", "zpq_kernels4.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_abi.cu"]
+CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_abi.cu"]
 CPP = ["zpq_model.cpp", "zpq_method.cpp", "zpq_frame.cpp", "zpq_hcomp.cpp"]
 
 

@@ -69,9 +69,10 @@ struct zpq_ctx {
   int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
   int wave_variant = 25;       // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps, bit 4 nibble-unrolled ICM / ISSE loop
   int dec_variant = 31;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7 or 15) slot-scheduled hashes, bit 3 (15) MATCH in warp A, bit 4 (31) register-resident predictions in warp B
+  int wave_role_major = 1;     // ZPQ_WAVE_ORDER: 1 = role-major warp order of the wavefront encoder (default), 0 = group-major (round 1)
   bool wave_prof = false;      // ZPQ_WAVE_PROF=1: per-role warp cycles of the wavefront encoder to stderr
   int dec_kernel = 7;           // ZPQ_DEC_KERNEL: 7 = critical-first two-warp decoder (zpq_kernels7.cu), 6 = round-1 two-warp decoder
-  int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 fast, 3 one-warp pipeline, 4 team, 5 wavefront encoder
+  int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 one-warp fast kernel, 5 production (wavefront encoder, two-warp decoder)
 };
 
 namespace {
@@ -174,17 +175,14 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     }
     if (wave.empty()) { if (next < todo.size()) continue; break; }
     const int nb = (int)wave.size();
-    // kernel class per block: 0 = wavefront encoder (zpq_kernels5.cu), 1 = three-warp team encoder
-    // (zpq_kernels4.cu), 2 = one-warp skewed-pipeline encoder (zpq_kernels3.cu), 3 = fast sequential kernel
-    // (zpq_kernels2.cu; always used for decoding), 4 = generic kernel (zpq_kernels.cu).
-    // ZPQ_KERNEL caps the tier (A/B testing).
+    // kernel class per block: 0 = wavefront encoder (zpq_kernels5.cu), 3 = step-plan kernels (the two-warp decoders
+    // zpq_kernels7.cu / zpq_kernels6.cu, or the one-warp kernel zpq_kernels2.cu for both directions), 4 = generic kernel
+    // (zpq_kernels.cu).  ZPQ_KERNEL caps the tier (A/B testing): 1 generic, 2 one-warp fast kernel, 5 production.
     const int kv = ctx->kernel_version;
     auto kclass = [&](int i) -> int {
       const ZModel& Mi = models[jobs[i].model];
       if (kv == 1) return 4;
       if (!decode && kv >= 5 && Mi.wave.ok) return 0;
-      if (!decode && kv >= 4 && Mi.team.ok) return 1;
-      if (!decode && kv >= 3 && Mi.pipe.ok) return 2;
       return Mi.fast.ok ? 3 : 4;
     };
     // class first, then model: the wavefront encoder wants 32 blocks of one model per warp
@@ -218,8 +216,13 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     const int nseg = (int)seg_len.size();
 
     if (!dev_io) {
-      CK(ctx->d_in.reserve(in_bytes + 16), "input staging cudaMalloc");
-      CK(ctx->d_out.reserve(out_bytes + 16), "output staging cudaMalloc");
+      // a staging buffer that does not fit fails the blocks of this wave (ZPQ_E_NOMEM), not the batch
+      if (ctx->d_in.reserve(in_bytes + 16) != cudaSuccess || ctx->d_out.reserve(out_bytes + 16) != cudaSuccess) {
+        cudaGetLastError();
+        for (int i : wave) jobs[i].status = ZPQ_E_NOMEM;
+        ctx->err = "Out of memory";
+        continue;
+      }
     }
     // meta: models | blocks | progs | seg_len | seg_out | status | out_len | first | counter
     uint64_t off = 0;
@@ -321,6 +324,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           Wv.hash_loop = (ctx->wave_variant & 16) ? 1 : 0;       // bit 4: nibble-unrolled ICM / ISSE loop
           Wv.mix_batch = (ctx->wave_variant & 8) ? 1 : 0;        // bit 3: byte-batched MIX warps
           Wv.mix_threads = (ctx->wave_variant & 4) ? 1 : 0;
+          Wv.role_major = ctx->wave_role_major;
           for (int k = first; k < first + cnt && Wv.mix_threads; ++k) {
             const ZModel& Mk = models[jobs[wave[k]].model];
             for (uint32_t ci = 0; ci < Mk.n; ++ci)
@@ -348,13 +352,9 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           uint32_t pw = 16;
           for (int k = first; k < first + cnt; ++k) pw = std::max(pw, models[jobs[wave[k]].model].fast.pw_bytes);
           const uint64_t room = ZPQ_SMEM_MAX - (uint64_t)zpq_code2_static_smem();
-          if (cls == 1) {
-            const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room / (pw + 16)));
-            CK(zpq_launch_enc4(&Ak, cnt, ctx->sm_count, teams, (int)pw, st), "zpq_enc_kernel4 launch");
-          } else {
+          {
             const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, room / pw));
-            if (cls == 2) CK(zpq_launch_enc3(&Ak, cnt, ctx->sm_count, warps, (int)pw, st), "zpq_enc_kernel3 launch");
-            else {
+            {
               unsigned long long sig = zpq_code2_signature(&models[jobs[wave[first]].model].fast);
               for (int k = first + 1; k < first + cnt; ++k)
                 if (zpq_code2_signature(&models[jobs[wave[k]].model].fast) != sig) { sig = 0; break; }
@@ -500,6 +500,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 31) ctx->wave_variant = v; }
   if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if ((v >= 0 && v <= 3) || v == 7 || v == 15 || v == 31) ctx->dec_variant = v; }
   if (const char* dk = getenv("ZPQ_DEC_KERNEL")) { const int v = atoi(dk); if (v == 6 || v == 7) ctx->dec_kernel = v; }
+  if (const char* wo = getenv("ZPQ_WAVE_ORDER")) ctx->wave_role_major = atoi(wo) != 0;
   if (const char* wp = getenv("ZPQ_WAVE_PROF")) ctx->wave_prof = atoi(wp) != 0;
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZPQ_E_CUDA; }
@@ -699,6 +700,10 @@ static int64_t comment_size_hint(const uint8_t* arc, const SegmentView& s) {
   const uint8_t* c = arc + s.comment_off;
   while (k < s.comment_len && c[k] >= '0' && c[k] <= '9' && k < 12) v = v * 10 + (c[k++] - '0');
   if (k == 0 || (k < s.comment_len && c[k] != ' ')) return -1;
+  // the comment is untrusted: a size that no coder could have produced from this many coded bytes (the arithmetic coder
+  // spends at least ~1/700 byte per input byte on fully predicted data; 2^16 x is far beyond that), or beyond the 2^31
+  // block limit, is not a hint -- the block then goes through the grow-until-it-fits staging path
+  if (v > ((uint64_t)1 << 31) - 4096 || v > (s.coded_len + 64) * 65536ull) return -1;
   return (int64_t)v;
 }
 
@@ -789,7 +794,8 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
     while (!pending.empty()) {
       std::vector<IJob> sub;
       for (size_t i : pending) {
-        tmp[i].resize(cap[i]);
+        try { tmp[i].resize(cap[i]); }
+        catch (const std::bad_alloc&) { jobs[i].status = ZPQ_E_NOMEM; tmp[i].clear(); tmp[i].resize(16); cap[i] = 16; }
         IJob J = jobs[i];
         J.out = tmp[i].data(); J.out_cap = cap[i]; J.out_skip = 0;
         sub.push_back(J);
@@ -799,6 +805,7 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
       std::vector<size_t> again;
       for (size_t k = 0; k < pending.size(); ++k) {
         const size_t i = pending[k];
+        if (jobs[i].status == ZPQ_E_NOMEM) continue;                   // its staging buffer could not be allocated above
         jobs[i].status = sub[k].status; jobs[i].out_len = sub[k].out_len; jobs[i].seg_out = sub[k].seg_out;
         jobs[i].first_byte = tmp[i].empty() ? -1 : tmp[i][0];
         if (sub[k].status == ZPQ_E_OUTPUT_FULL && cap[i] < ((uint64_t)1 << 31)) {
@@ -854,7 +861,9 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
           if (!verify_sha1 || pos[i] + total_i > out_cap || !out) continue;
           uint64_t at = pos[i];
           for (size_t s = 0; s < J.seg_out.size(); ++s) {
+            if (!is_prog[i] && s == 0 && J.seg_out[0] == 0) { st[i] = ZPQ_E_CORRUPT; break; }    // no room for the post-processor flag byte
             const uint64_t n = is_prog[i] ? post_seg[i][s] : J.seg_out[s] - (s == 0 ? 1 : 0);
+            if (at + n > out_cap) { st[i] = ZPQ_E_CORRUPT; break; }
             if (bv[i].segs[s].has_sha1) {
               uint8_t d[20];
               sha1_of(out + at, n, d);

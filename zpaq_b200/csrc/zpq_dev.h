@@ -159,7 +159,7 @@ struct ZHashPlan {
   uint32_t w2[ZPQ_HSLOTS][32];           // ZH_WORD: second word (multiplier, first flag)
 };
 
-// Team plan (zpq_kernels4.cu): the skewed pipeline of ZPipe split over THREE warps per block so that
+// Team plan (round-1 three-warp encoder, removed; the wavefront encoder still reads nmix / mix_comp): the skewed pipeline of ZPipe split over THREE warps per block so that
 // the block's instruction stream is issued by three schedulers at once:
 //   role 0 = every ICM / ISSE component (one code path, no divergence)
 //   role 1 = every MIX component (lane l = input l, cooperative dot product)
@@ -194,9 +194,9 @@ struct ZModel {
   ZFill fills[ZPQ_MAX_FILLS];
   // ---- fast kernel plan (zpq_kernels2.cu) ----
   ZFast fast;
-  // ---- skewed-pipeline encode plan (zpq_kernels3.cu) ----
+  // ---- pipeline depths of the components (wavefront encoder; dist_byte is read by the decoders too) ----
   ZPipe pipe;
-  // ---- three-warp team plan (zpq_kernels4.cu) ----
+  // ---- role split / mixer list (wavefront encoder's MIX warps) ----
   ZTeam team;
   // ---- wavefront encode plan (zpq_kernels5.cu) ----
   ZWave wave;
@@ -257,6 +257,7 @@ struct ZWaveArgs {
   unsigned long long* prof;              // optional [32][2]: cycles and warp count per role (ZPQ_WAVE_PROF=1), else null
   int hash_loop;                         // 1: ICM / ISSE component threads run the nibble-unrolled loop (zpq_kernels5.cu)
   int mix_batch;                         // 1: MIX warps mix the eight bits of a byte together (full-mask mixers; zpq_kernels5.cu)
+  int role_major;                        // 1: warp index = component * ngroups + group (role-homogeneous CTAs), 0: group * ncs + component
   int mix_threads;                       // 1: every MIX of the launch has a full c8 mask and >= 256 weight sets and is coded
                                          // by a component thread (eight independent rows per byte); 0: one warp per (block, MIX)
 };

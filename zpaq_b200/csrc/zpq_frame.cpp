@@ -103,6 +103,7 @@ int scan_archive(const uint8_t* a, uint64_t n, std::vector<BlockView>* blocks, s
     pos += 2;
     const int hsize = a[pos] + 256 * a[pos + 1];
     if (pos + 2 + (uint64_t)hsize > n) return bad(err, "unexpected end of file", ZPQ_E_EOF);
+    if (hsize < 6) return bad(err, "invalid block header", ZPQ_E_HEADER);   // hh hm ph pm n ... END: the component count is read below
     B.hdr_off = pos; B.hlen = hsize + 2;
     pos += (uint64_t)hsize + 2;
     for (;;) {

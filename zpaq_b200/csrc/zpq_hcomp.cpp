@@ -16,6 +16,7 @@
 // the device (vm_run), so foreign or hand-written models stay exact.
 #include "zpq_host.h"
 #include <string.h>
+#include <new>
 
 namespace zpq {
 namespace {
@@ -574,6 +575,8 @@ void build_hash_plan(ZModel* M) {
 int postprocess_block(int ph, int pm, const uint8_t* model_out, const uint64_t* seg_len, int nseg,
                       std::vector<uint8_t>* payload, std::vector<uint64_t>* seg_payload, std::string* err) {
   payload->clear(); seg_payload->assign((size_t)std::max(nseg, 0), 0);
+  // ZPAQL::init (libzpaq.cpp:1009-1024) rejects these sizes ("H too big" / "M too big"); 1 << 255 is not a size
+  if (ph < 0 || ph > 32 || pm < 0 || pm > 32) { if (err) *err = "H or M too big"; return ZPQ_E_COMPONENT; }
   int state = 0;                 // 0 first byte, 1 PASS, 2/3 length bytes, 4 program bytes, 5 running
   size_t want = 0;
   std::vector<uint8_t> prog;
@@ -599,7 +602,8 @@ int postprocess_block(int ph, int pm, const uint8_t* model_out, const uint64_t* 
         case 4:
           prog.push_back((uint8_t)c);
           if (prog.size() == want) {
-            vm = new HostVm(ph, pm, prog.data(), (int)prog.size());     // ZPAQL::initp: H = 2^ph words, M = 2^pm bytes
+            try { vm = new HostVm(ph, pm, prog.data(), (int)prog.size()); }     // ZPAQL::initp: H = 2^ph words, M = 2^pm bytes
+            catch (const std::bad_alloc&) { if (err) *err = "Out of memory"; return ZPQ_E_NOMEM; }
             vm->out = payload; vm->max_steps = (long long)1 << 40;
             state = 5;
           }

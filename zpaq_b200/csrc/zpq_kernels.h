@@ -23,8 +23,6 @@ int zpq_dec7_ctrl_bytes(void);
 int zpq_dec7_takes(unsigned long long sig);
 cudaError_t zpq_launch_dec7(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, unsigned long long sig, cudaStream_t st);
 cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant);
-cudaError_t zpq_launch_enc4(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, cudaStream_t st);
-cudaError_t zpq_launch_enc3(const ZKernelArgs* a, int nblk, int sm_count, int warps, int pw_bytes, cudaStream_t st);
 unsigned long long zpq_code2_signature(const ZFast* F);
 cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int decode, int sm_count, int warps, int pw_bytes,
                              unsigned long long sig, cudaStream_t st);

@@ -1,6 +1,6 @@
 // zpq_kernels5.cu -- wavefront ENCODE for sm_100a: one thread per (block, component).
 //
-// Encoding is a feed-forward pipeline over components (zpq_kernels3.cu header): no component reads a
+// Encoding is a feed-forward pipeline over components: while compressing, the coded bit is input data, so no component reads a
 // later component's output or the coder's state.  Here the pipeline is unrolled in TIME over kernel
 // launches instead of over lanes of one warp:
 //
@@ -66,7 +66,10 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
     // =======================================================================================
     // thread = (block, component) ; warp = one component of the 32 blocks of a group
     // =======================================================================================
-    const int g = gw / NCS, c = gw - g * NCS;
+    // role-major order (W.role_major): consecutive warps -- and so the warps of a CTA and of neighbouring CTAs -- run the
+    // SAME component of different groups, i.e. the same code: the instruction caches of an SM then hold one or two roles
+    // instead of all of them (ncu of the group-major order: 7 of 19.6 stall cycles per instruction were instruction fetches)
+    const int g = W.role_major ? gw % W.ngroups : gw / NCS, c = W.role_major ? gw / W.ngroups : gw - g * NCS;
     const int cnt = (int)W.group_count[g];
     if (lane >= cnt) return -1;
     const int bi = (int)W.group_first[g] + lane;

@@ -1,14 +1,17 @@
 // zpq_method.cpp -- SURVEY.md 8(a) row C1: model selection feeding the hot path.
 //
-// method string (+ block payload) -> block header bytes, for the context-model
-// family only (no LZ77/BWT/E8E9 pre-processing, no PCOMP).  Restates
-//   * libzpaq::compressBlock's expansion of digit methods (libzpaq.cpp:7556-7691),
-//     including the data-dependent period analysis of level 5 (7655-7688),
-//   * makeConfig's context-model section (libzpaq.cpp:7325-7534),
-//   * the byte encoding the Compiler gives that ZPAQL source (libzpaq.cpp:2570-2690).
-// Instead of generating ZPAQL text and tokenising it again, the COMP and HCOMP
-// bytes are emitted directly by a small structured assembler.  Output is pinned
-// byte for byte by tests/golden/headers.json (made with the unmodified reference).
+// method string (+ block payload) -> block header bytes, for the context-model family only (no LZ77 / BWT / E8E9
+// pre-processing, no PCOMP).  The output has to equal what libzpaq::compressBlock -> makeConfig -> Compiler write for
+// the same method (libzpaq.cpp:7543-7691, 7325-7534, 2570-2690) and is pinned byte for byte by tests/golden/headers.json
+// (168 headers made with the unmodified reference) plus a fuzz test against the live reference on the GPU box.
+//
+// Structure (this file's own, not the reference's text-generating flow):
+//   1. tokenize()        method text  -> tokens {letter, numeric arguments}
+//   2. level_tokens()    digit methods ("4", "50", "5,R,T") -> the same token list a spelled-out method would give;
+//                        level 5 asks dominant_gaps() for up to two periodic structures in the payload
+//   3. family builders   one per token letter, looked up in kFamilies: each appends component records and HCOMP code to a
+//                        Draft.  HCOMP code is assembled from opcode tables with parameter slots (Snip), not from ZPAQL text
+//   4. serialise()       Draft -> header bytes
 #include "zpq_host.h"
 #include <ctype.h>
 #include <string.h>
@@ -16,14 +19,122 @@
 namespace zpq {
 namespace {
 
-int lg(unsigned x) {   // floor(log2(x))+1, 0 for 0   (libzpaq.cpp:6566)
-  int r = 0;
-  while (x) { ++r; x >>= 1; }
-  return r;
-}
-int popcount(unsigned x) { int r = 0; for (; x; x >>= 1) r += x & 1; return r; }
+// ---------------------------------------------------------------- small helpers
+int bit_length(unsigned x) { int r = 0; for (; x; x >>= 1) ++r; return r; }           // 0 -> 0, 1 -> 1, 255 -> 8, 256 -> 9
+int ones(unsigned x) { int r = 0; for (; x; x &= x - 1) ++r; return r; }
 
-// ZPAQL opcodes used by the generator (indices of opcodelist, libzpaq.cpp:2456-2491)
+// ---------------------------------------------------------------- 1. tokens
+struct Token {
+  char letter = 0;
+  std::vector<int> arg;
+  int at(size_t i, int dflt) const { return i < arg.size() ? arg[i] : dflt; }
+};
+
+// A token is one character followed -- only if the very next character is a digit -- by numbers separated by ',' or '.'.
+// A separator opens a new (zero) number, digits extend the last one; anything else ends the token.  Characters that are
+// not family letters become tokens too and are ignored later, exactly as stray characters are in the reference's scan.
+std::vector<Token> tokenize(const char* s) {
+  std::vector<Token> out;
+  while (*s) {
+    Token t;
+    t.letter = *s++;
+    if (isdigit((unsigned char)*s)) {
+      t.arg.push_back(0);
+      for (; isdigit((unsigned char)*s) || *s == ',' || *s == '.'; ++s) {
+        if (isdigit((unsigned char)*s)) t.arg.back() = t.arg.back() * 10 + (*s - '0');
+        else t.arg.push_back(0);
+      }
+    }
+    out.push_back(t);
+  }
+  return out;
+}
+Token tok(char letter, std::initializer_list<int> a = {}) { Token t; t.letter = letter; t.arg.assign(a.begin(), a.end()); return t; }
+
+// ---------------------------------------------------------------- 2. digit methods
+// Gap statistics of level 5 (libzpaq.cpp:7655-7688).  For every byte the distance to the previous byte of the same value
+// is counted (1 .. 4095).  A "dominant gap" is the distance g >= 5 with the largest share hist[g] / (256 + pool - seen),
+// where pool = bytes not explained by gaps 1..3 (nor by an earlier dominant gap) and seen = the counts of the gaps
+// 5 .. g-1; the scan stops once seen reaches pool.  A gap is accepted when its share exceeds 0.1; at most two are taken,
+// the second after removing the first from the statistics.
+std::vector<int> dominant_gaps(const uint8_t* p, unsigned n) {
+  enum { kGaps = 1 << 12 };
+  std::vector<int> hist(kGaps, 0);
+  int last_seen[256];
+  memset(last_seen, 0, sizeof(last_seen));
+  for (unsigned i = 0; i < n; ++i) {
+    const int gap = (int)i - last_seen[p[i]];
+    if (gap > 0 && gap < kGaps) ++hist[gap];
+    last_seen[p[i]] = (int)i;
+  }
+  std::vector<int> found;
+  int pool = (int)n - hist[1] - hist[2] - hist[3];
+  while (found.size() < 2) {
+    int best = 0, seen = 0;
+    double best_share = 0;
+    for (int g = 5; g < kGaps && seen < pool; ++g) {
+      const double share = hist[g] / (256.0 + pool - seen);
+      if (share > best_share) { best_share = share; best = g; }
+      seen += hist[g];
+    }
+    if (best <= 4 || !(best_share > 0.1)) break;
+    found.push_back(best);
+    pool -= hist[best];
+    hist[best] = 0;
+  }
+  return found;
+}
+
+// "LB[,R,T]": L = level digit, B = block size digits (ignored here: the block decides), R,T -> block type R*4+T
+// (bit 0 text, bit 1 exe; 512 when no type is given).  Only the context-mixing branches of levels 4 and 5 are in scope.
+int level_tokens(const std::string& m, const uint8_t* p, uint64_t n64, int* arg0, std::vector<Token>* out, std::string* err) {
+  const unsigned n = (unsigned)n64;
+  *arg0 = std::max(bit_length(n + 4095) - 20, 0);
+  int field[4] = {0, 0, 0, 0}, nsep = 0;
+  for (size_t i = 1; i < m.size() && nsep < 4; ++i) {
+    if (m[i] == ',' || m[i] == '.') ++nsep;
+    else if (isdigit((unsigned char)m[i])) field[nsep] = field[nsep] * 10 + (m[i] - '0');
+  }
+  const unsigned type = nsep == 0 ? 512u : (unsigned)(field[1] * 4 + field[2]);
+  const bool text = (type & 1u) != 0, exe = (type & 2u) != 0;
+  const int level = m[0] - '0';
+  if (level <= 3) { *err = "levels 0-3 use LZ77/BWT pre-processing, which is outside the context-mixing path"; return ZPQ_E_METHOD; }
+  if (level == 4 && (type < 48 || type >= 900)) {
+    *err = "level 4 selects store/LZ77/BWT for this block type: outside the context-mixing path"; return ZPQ_E_METHOD;
+  }
+  if (exe) { *err = "E8E9 pre-processing (exe block type) is outside the context-mixing path"; return ZPQ_E_METHOD; }
+  std::vector<Token>& t = *out;
+  t.clear();
+  if (level == 4) {
+    // order 0..5 chain, match model, optional word model, one mixer
+    t.push_back(tok('c'));
+    t.push_back(tok('i', {1, 1, 1, 1, 2}));
+    t.push_back(tok('a'));
+    if (text) t.push_back(tok('w'));
+    t.push_back(tok('m'));
+    return ZPQ_OK;
+  }
+  // level 5: word model (two links plus a line-position context for text), order-0 CM, order 0..8 chain, match model,
+  // up to two periodic models, three sparse contexts, two mixers, a final MIX2 / SSE / MIX2 stage
+  if (text) { t.push_back(tok('w', {2})); t.push_back(tok('c', {0, 1010, 255})); t.push_back(tok('i', {1})); }
+  else { t.push_back(tok('w', {1})); t.push_back(tok('i', {1})); }
+  t.push_back(tok('c', {256}));
+  t.push_back(tok('c'));
+  t.push_back(tok('i', {1, 1, 1, 1, 1, 1, 2}));
+  t.push_back(tok('a'));
+  for (int gap : dominant_gaps(p, n)) {
+    t.push_back(tok('c', {0, 0, 999 + gap, 255})); t.push_back(tok('i', {1}));            // the byte one period back
+    if (gap <= 255) { t.push_back(tok('c', {0, gap})); t.push_back(tok('i', {1})); }      // position inside the period
+  }
+  t.push_back(tok('c', {0, 2, 0, 255})); t.push_back(tok('i', {1}));
+  t.push_back(tok('c', {0, 3, 0, 0, 255})); t.push_back(tok('i', {1}));
+  t.push_back(tok('c', {0, 4, 0, 0, 0, 255})); t.push_back(tok('i', {1}));
+  t.push_back(tok('m')); t.push_back(tok('m', {16})); t.push_back(tok('t')); t.push_back(tok('s', {19})); t.push_back(tok('t', {0}));
+  return ZPQ_OK;
+}
+
+// ---------------------------------------------------------------- 3. draft model and HCOMP assembly
+// ZPAQL opcodes used by the generator (indexes of the opcode list, libzpaq.cpp:2456-2491)
 enum {
   A_INC = 1, A_ZERO = 4, A_R = 7, B_INC = 9, C_DEC = 18, D_INC = 25, PD_ZERO = 52, JT = 39, JF = 47, R_A = 55,
   HALT = 56, HASH = 59, HASHD = 60, JMP = 63,
@@ -33,102 +144,210 @@ enum {
   AND_N = 175, SHL_N = 207, SHR_N = 215, EQ_N = 223, LT_N = 231, GT_N = 239
 };
 
-struct Asm {
-  std::vector<uint8_t> b;
-  std::vector<size_t> ifs;
+// One instruction of a snippet: opcode, then NONE, a literal operand 0..255, or P(k) = the k-th parameter of the call.
+// IF / ELSE / ENDIF are pseudo-ops resolved to the short forward jumps the Compiler writes (libzpaq.cpp:2580-2622).
+enum { NONE = -1, IF_ = 1000, ELSE_ = 1001, ENDIF_ = 1002 };
+constexpr int P(int k) { return 256 + k; }
+struct Snip { int op; int operand; };
+
+struct Record { int type; int a[5]; };          // one COMP entry: type byte and up to five arguments
+
+struct Draft {
+  std::vector<Record> comps;
+  std::vector<uint8_t> code;
+  std::vector<size_t> open_jumps;               // operand positions of JF / JMP waiting for their target
   bool ok = true;
-  void op(int o) { b.push_back((uint8_t)o); }
-  void op(int o, int n) { if (n < 0 || n > 255) ok = false; b.push_back((uint8_t)o); b.push_back((uint8_t)n); }
-  // IF / ELSE / ENDIF as the Compiler encodes them (libzpaq.cpp:2580-2622): short forward jumps
-  void if_() { b.push_back(JF); b.push_back(0); ifs.push_back(b.size() - 1); }
-  void else_() {
-    if (ifs.empty()) { ok = false; return; }
-    const size_t a = ifs.back(); ifs.pop_back();
-    const size_t j = b.size() - a + 1;
-    if (j > 127) ok = false;
-    b[a] = (uint8_t)j;
-    b.push_back(JMP); b.push_back(0); ifs.push_back(b.size() - 1);
+  int membits = 20;                             // log2 of the block size class
+  int sb = 5;                                   // running "size bits" hint handed from one family to the next
+
+  int count() const { return (int)comps.size(); }
+  void component(int type, int a1 = -1, int a2 = -1, int a3 = -1, int a4 = -1, int a5 = -1) {
+    static const int kBytes[10] = {0, 2, 3, 2, 3, 4, 6, 6, 3, 5};
+    Record r{type, {a1, a2, a3, a4, a5}};
+    for (int i = 0; i + 1 < kBytes[type]; ++i) if (r.a[i] < 0 || r.a[i] > 255) ok = false;
+    comps.push_back(r);
   }
-  void endif_() {
-    if (ifs.empty()) { ok = false; return; }
-    const size_t a = ifs.back(); ifs.pop_back();
-    const size_t j = b.size() - a - 1;
-    if (j > 127) ok = false;
-    b[a] = (uint8_t)j;
+  void byte(int v) { if (v < 0 || v > 255) ok = false; code.push_back((uint8_t)v); }
+  void close_jump(size_t extra) {
+    if (open_jumps.empty()) { ok = false; return; }
+    const size_t at = open_jumps.back(); open_jumps.pop_back();
+    const size_t dist = code.size() - at - 1 + extra;
+    if (dist > 127) ok = false;
+    code[at] = (uint8_t)dist;
+  }
+  template <size_t N> void emit(const Snip (&s)[N], std::initializer_list<int> params = {}) {
+    for (const Snip& i : s) {
+      if (i.op == IF_) { code.push_back(JF); code.push_back(0); open_jumps.push_back(code.size() - 1); continue; }
+      if (i.op == ELSE_) { close_jump(2); code.push_back(JMP); code.push_back(0); open_jumps.push_back(code.size() - 1); continue; }
+      if (i.op == ENDIF_) { close_jump(0); continue; }
+      code.push_back((uint8_t)i.op);
+      if (i.operand == NONE) continue;
+      if (i.operand < 256) byte(i.operand);
+      else {
+        const size_t k = (size_t)(i.operand - 256);
+        byte(k < params.size() ? *(params.begin() + k) : -1);
+      }
+    }
   }
 };
 
-struct Comp {
-  std::vector<uint8_t> b;
-  bool ok = true;
-  void add(int type, int a1 = -1, int a2 = -1, int a3 = -1, int a4 = -1, int a5 = -1) {
-    b.push_back((uint8_t)type);
-    const int a[5] = {a1, a2, a3, a4, a5};
-    static const int len[10] = {0, 2, 3, 2, 3, 4, 6, 6, 3, 5};
-    for (int i = 0; i < len[type] - 1; ++i) { if (a[i] < 0 || a[i] > 255) ok = false; b.push_back((uint8_t)a[i]); }
+// every program starts by pushing the new byte into the M ring and remembering where that byte value was last seen
+const Snip kProlog[] = {{C_DEC, NONE}, {PC_A, NONE}, {ADD_N, 255}, {D_A, NONE}, {PD_C, NONE}};
+const Snip kClearH[] = {{D_N, P(0)}, {PD_ZERO, NONE}};                                   // H[p0] = 0
+const Snip kPosAnd[] = {{A_C, NONE}, {AND_N, P(0)}, {HASHD, NONE}};                      // position & (2^k - 1)
+const Snip kPosMod[] = {{A_C, NONE}, {MOD_N, P(0)}, {HASHD, NONE}};                      // position % period
+const Snip kLastSeen[] = {{A_N, 255}, {ADD_N, P(0)}, {D_A, NONE}, {A_PD, NONE}, {SUB_C, NONE}, {GT_N, 255}, {IF_, NONE},
+                          {A_N, 255}, {ENDIF_, NONE}, {D_N, P(1)}, {HASHD, NONE}};      // min(255, distance to the last byte p0)
+const Snip kByteFull[] = {{A_PB, NONE}, {HASHD, NONE}};
+const Snip kByteMasked[] = {{A_PB, NONE}, {AND_N, P(0)}, {HASHD, NONE}};
+// LZ77 parse-state context (R1 = state, R2 = literal-or-length byte); p0 = literal mask
+const Snip kParseMasked[] = {{A_R, 1}, {GT_N, 1}, {IF_, NONE}, {A_R, 2}, {LT_N, 64}, {IF_, NONE}, {A_PB, NONE}, {AND_N, P(0)}, {HASHD, NONE},
+                             {ELSE_, NONE}, {SHR_N, 6}, {HASHD, NONE}, {A_R, 1}, {HASHD, NONE}, {ENDIF_, NONE},
+                             {ELSE_, NONE}, {A_N, 255}, {HASHD, NONE}, {A_R, 2}, {HASHD, NONE}, {ENDIF_, NONE}};
+const Snip kParseFull[] = {{A_R, 1}, {GT_N, 1}, {IF_, NONE}, {A_R, 2}, {LT_N, 64}, {IF_, NONE}, {A_PB, NONE}, {HASHD, NONE},
+                           {ELSE_, NONE}, {SHR_N, 6}, {HASHD, NONE}, {A_R, 1}, {HASHD, NONE}, {ENDIF_, NONE},
+                           {ELSE_, NONE}, {A_N, 255}, {HASHD, NONE}, {A_R, 2}, {HASHD, NONE}, {ENDIF_, NONE}};
+const Snip kSkipFar[] = {{A_N, P(0)}, {SHL_N, 8}, {ADD_N, P(1)}, {ADD_B, NONE}, {B_A, NONE}};      // b += p0 * 256 + p1
+const Snip kSkipNear[] = {{A_N, P(0)}, {ADD_B, NONE}, {B_A, NONE}};                                // b += p0
+const Snip kPackOpen[] = {{D_N, P(0)}, {PD_ZERO, NONE}, {B_C, NONE}, {A_ZERO, NONE}};
+const Snip kPackByte[] = {{SHL_N, 8}, {ADD_PB, NONE}};
+const Snip kPackPart[] = {{SHL_N, 8}, {ADD_PB, NONE}, {SHR_N, P(0)}};
+const Snip kPackClose[] = {{SHL_N, 8}, {PD_A, NONE}};
+const Snip kChainOpen[] = {{D_N, P(0)}, {B_C, NONE}, {A_PD, NONE}, {D_INC, NONE}};                 // a = H[p0], d = p0 + 1, b = newest byte
+const Snip kRoll[] = {{A_PD, NONE}, {MUL_N, P(0)}, {ADD_PC, NONE}, {A_INC, NONE}, {PD_A, NONE}};   // H[d] = H[d] * p0 + byte + 1
+const Snip kWordTest[] = {{A_PC, NONE}, {AND_N, P(0)}, {SUB_N, P(1)}, {AND_N, 255}, {LT_N, P(2)}, {IF_, NONE}};
+const Snip kShiftDown[] = {{D_N, P(0)}, {A_PD, NONE}, {D_INC, NONE}, {PD_A, NONE}};                // H[p0 + 1] = H[p0]
+
+void one(Draft& d, int op) { d.code.push_back((uint8_t)op); }
+void one(Draft& d, int op, int n) { d.code.push_back((uint8_t)op); d.byte(n); }
+
+// 'c': an ICM (count limit 0) or CM whose context is built from an optional positional term and masked recent bytes.
+//   args: [limit*? + slot bits], [special], [byte selectors ...]
+//   special 2..255: position modulo it; 1000..1255: distance to the last occurrence of byte (special - 1000)
+//   selector 255 / 1..254: that byte, whole or masked; 0: skip it; 256..511: LZ77 parse state (mask = selector - 256);
+//   1001..: skip (selector - 1000) bytes
+void family_context(Draft& d, const Token& t) {
+  const int spec0 = t.at(0, 0), special = t.at(1, 0);
+  int bits = 11 + (special < 256 ? bit_length((unsigned)special) : 6);
+  for (size_t i = 2; i < t.arg.size(); ++i) if (t.arg[i] < 512) bits += ones((unsigned)t.arg[i]) * 3 / 4;
+  d.sb = std::min(bits, d.membits);
+  const int me = d.count();
+  if (spec0 % 1000 == 0) d.component(ZT_ICM, d.sb - 6 - spec0 / 1000);
+  else d.component(ZT_CM, d.sb - 2 - spec0 / 1000, spec0 % 1000 - 1);
+  d.emit(kClearH, {me});
+  if (special > 1 && special <= 255) {
+    const bool pow2 = bit_length((unsigned)special) != bit_length((unsigned)special - 1);
+    if (pow2) d.emit(kPosAnd, {special - 1}); else d.emit(kPosMod, {special});
   }
+  else if (special >= 1000 && special <= 1255) d.emit(kLastSeen, {special - 1000, me});
+  for (size_t i = 2; i < t.arg.size(); ++i) {
+    const int sel = t.arg[i];
+    if (i == 2) one(d, B_C);
+    if (sel == 255) d.emit(kByteFull);
+    else if (sel > 0 && sel < 255) d.emit(kByteMasked, {sel});
+    else if (sel >= 256 && sel < 511) d.emit(kParseMasked, {sel - 256});
+    else if (sel == 511) d.emit(kParseFull);
+    else if (sel >= 1256) d.emit(kSkipFar, {((sel - 1000) >> 8) & 255, (sel - 1000) & 255});
+    else if (sel > 1000) d.emit(kSkipNear, {sel - 1000});
+    if (sel < 512 && i + 1 < t.arg.size()) one(d, B_INC);
+  }
+}
+
+// 'm' / 't' / 's': MIX over everything so far, MIX2 / SSE over the last component(s).  A context wider than 8 bits packs
+// whole recent bytes (and one partial byte) above the c8 byte.
+void family_final(Draft& d, const Token& t) {
+  const int have = d.count();
+  if (have <= (t.letter == 't' ? 1 : 0)) return;
+  int width = t.at(0, 8);
+  const int rate = t.at(1, t.letter == 's' ? 32 : 24);
+  d.sb = 5 + width * 3 / 4;
+  if (t.letter == 'm') d.component(ZT_MIX, width, 0, have, rate, 255);
+  else if (t.letter == 't') d.component(ZT_MIX2, width, have - 1, have - 2, rate, 255);
+  else d.component(ZT_SSE, width, have - 1, rate, t.at(2, 255));
+  if (width <= 8) return;
+  d.emit(kPackOpen, {have});
+  for (; width >= 16; width -= 8) {
+    d.emit(kPackByte);
+    if (width > 16) one(d, B_INC);
+  }
+  if (width > 8) d.emit(kPackPart, {16 - width});
+  d.emit(kPackClose);
+}
+
+// 'i': a chain of ISSE links, each hashing (arg % 10) more bytes on top of the previous link's context
+void family_chain(Draft& d, const Token& t) {
+  if (d.count() == 0) return;
+  d.emit(kChainOpen, {d.count() - 1});
+  for (size_t i = 0; i < t.arg.size() && d.count() < 254; ++i) {
+    const int more = t.arg[i] % 10;
+    const bool last_link = i + 1 == t.arg.size();
+    for (int j = 0; j < more; ++j) {
+      one(d, HASH);
+      if (!last_link || j + 1 < more) one(d, B_INC);
+      d.sb += 6;
+    }
+    one(d, PD_A);
+    if (!last_link) one(d, D_INC);
+    d.sb = std::min(d.sb, d.membits);
+    d.component(ZT_ISSE, d.sb - 6 - t.arg[i] / 10, d.count() - 1);
+  }
+}
+
+// 'a': MATCH with a rolling hash of multiplier arg0
+void family_match(Draft& d, const Token& t) {
+  const int mult = t.at(0, 24), buf_less = t.at(1, 0), idx_less = t.at(2, 0);
+  const int me = d.count();
+  d.component(ZT_MATCH, d.membits - idx_less - 2, d.membits - buf_less);
+  one(d, D_N, me);
+  d.emit(kRoll, {mult});
+  d.sb = 5 + (d.membits - buf_less) * 3 / 4;
+}
+
+// 'w': word model -- an ICM and (links - 1) ISSE over rolling hashes of the current and previous words; a byte b is a
+// letter when ((b & mask) - first) mod 256 < span
+void family_word(Draft& d, const Token& t) {
+  const int links = t.at(0, 1), first = t.at(1, 65), span = t.at(2, 26), mask = t.at(3, 223), mult = t.at(4, 20), less = t.at(5, 0);
+  const int me = d.count();
+  d.component(ZT_ICM, d.membits - 6 - less);
+  for (int i = 1; i < links; ++i) d.component(ZT_ISSE, d.membits - 6 - less, me + i - 1);
+  d.emit(kWordTest, {mask, first, span});
+  for (int i = 0; i < links; ++i) {                      // letter: extend every word hash
+    if (i == 0) one(d, D_N, me); else one(d, D_INC);
+    d.emit(kRoll, {mult});
+  }
+  const Snip kElse[] = {{ELSE_, NONE}};
+  d.emit(kElse);
+  for (int i = links - 1; i > 0; --i) d.emit(kShiftDown, {me + i - 1});     // word ends: hashes move one link down
+  d.emit(kClearH, {me});
+  const Snip kEnd[] = {{ENDIF_, NONE}};
+  d.emit(kEnd);
+  d.sb = d.membits - less;
+}
+
+struct Family { char letter; void (*build)(Draft&, const Token&); };
+const Family kFamilies[] = {
+  {'c', family_context}, {'m', family_final}, {'t', family_final}, {'s', family_final},
+  {'i', family_chain}, {'a', family_match}, {'w', family_word},
 };
 
-std::string itos(long long x) { char s[32]; snprintf(s, sizeof(s), "%lld", x); return s; }
-
-// compressBlock's expansion of "LB,R,t" digit methods (libzpaq.cpp:7556-7691).
-int expand_digit_method(const std::string& m, const uint8_t* p, uint64_t n64, std::string* out, std::string* err) {
-  const unsigned n = (unsigned)n64;
-  const int arg0 = std::max(lg(n + 4095) - 20, 0);
-  unsigned type = 0;
-  {
-    int commas = 0, arg[4] = {0, 0, 0, 0};
-    for (size_t i = 1; i < m.size() && commas < 4; ++i) {
-      if (m[i] == ',' || m[i] == '.') ++commas;
-      else if (isdigit((unsigned char)m[i])) arg[commas] = arg[commas] * 10 + m[i] - '0';
-    }
-    type = commas == 0 ? 512u : (unsigned)(arg[1] * 4 + arg[2]);
+// ---------------------------------------------------------------- 4. header bytes
+// hsize[2] hh hm ph pm n COMP 0 HCOMP 0   ("comp 9 16 0 0", libzpaq.cpp:7307)
+int serialise(const Draft& d, std::vector<uint8_t>* hdr, std::string* err) {
+  static const int kBytes[10] = {0, 2, 3, 2, 3, 4, 6, 6, 3, 5};
+  std::vector<uint8_t> comp;
+  for (const Record& r : d.comps) {
+    comp.push_back((uint8_t)r.type);
+    for (int i = 0; i + 1 < kBytes[r.type]; ++i) comp.push_back((uint8_t)r.a[i]);
   }
-  const int level = m[0] - '0';
-  const int doe8 = (type & 2) * 2;
-  std::string method = "x" + itos(arg0);
-  if (level <= 3) { *err = "levels 0-3 use LZ77/BWT pre-processing, which is outside the context-mixing path"; return ZPQ_E_METHOD; }
-  if (level == 4) {
-    if (type < 48 || type >= 900) { *err = "level 4 selects store/LZ77/BWT for this block type: outside the context-mixing path"; return ZPQ_E_METHOD; }
-    method += "," + itos(doe8) + "ci1,1,1,1,2a";
-    if (type & 1) method += "w";
-    method += "m";
-  }
-  else {
-    method += "," + itos(doe8);
-    if (type & 1) method += "w2c0,1010,255i1";
-    else method += "w1i1";
-    method += "c256ci1,1,1,1,1,1,2a";
-    // analyse the data: histogram of distances between equal bytes (libzpaq.cpp:7655-7666)
-    const int NR = 1 << 12;
-    std::vector<int> pt(256, 0), r(NR, 0);
-    for (unsigned i = 0; i < n; ++i) {
-      const int k = (int)i - pt[p[i]];
-      if (k > 0 && k < NR) ++r[k];
-      pt[p[i]] = (int)i;
-    }
-    int n1 = (int)n - r[1] - r[2] - r[3];
-    for (int i = 0; i < 2; ++i) {
-      int period = 0;
-      double score = 0;
-      int t = 0;
-      for (int j = 5; j < NR && t < n1; ++j) {
-        const double s = r[j] / (256.0 + n1 - t);
-        if (s > score) { score = s; period = j; }
-        t += r[j];
-      }
-      if (period > 4 && score > 0.1) {
-        method += "c0,0," + itos(999 + period) + ",255i1";
-        if (period <= 255) method += "c0," + itos(period) + "i1";
-        n1 -= r[period];
-        r[period] = 0;
-      }
-      else break;
-    }
-    method += "c0,2,0,255i1c0,3,0,0,255i1c0,4,0,0,0,255i1mm16ts19t0";
-  }
-  if (doe8) { *err = "E8E9 pre-processing (exe block type) is outside the context-mixing path"; return ZPQ_E_METHOD; }
-  *out = method;
+  const size_t hsize = 5 + comp.size() + 1 + d.code.size() + 1;
+  if (hsize > 65535) { *err = "program too big"; return ZPQ_E_METHOD; }
+  hdr->clear();
+  const uint8_t fixed[7] = {(uint8_t)(hsize & 255), (uint8_t)(hsize >> 8), 9, 16, 0, 0, (uint8_t)d.count()};
+  hdr->insert(hdr->end(), fixed, fixed + 7);
+  hdr->insert(hdr->end(), comp.begin(), comp.end());
+  hdr->push_back(0);
+  hdr->insert(hdr->end(), d.code.begin(), d.code.end());
+  hdr->push_back(0);
   return ZPQ_OK;
 }
 
@@ -139,177 +358,39 @@ int header_from_method(const char* method_, const uint8_t* data, uint64_t n, std
   if (!err) err = &e0;
   if (!method_ || !method_[0]) { *err = "empty method"; return ZPQ_E_METHOD; }
   if (n > 0x7fffffffull - 4096) { *err = "block too big"; return ZPQ_E_ARG; }
-  std::string ms = method_;
+  const std::string ms = method_;
+  std::vector<Token> tokens;
+  int size_class = 0, preprocessing = 0;
   if (isdigit((unsigned char)ms[0])) {
-    std::string x;
-    const int rc = expand_digit_method(ms, data, n, &x, err);
+    const int rc = level_tokens(ms, data, n, &size_class, &tokens, err);
     if (rc != ZPQ_OK) return rc;
-    ms = x;
   }
-  if (ms[0] != 'x') { *err = "Unsupported method"; return ZPQ_E_METHOD; }
-
-  // ---- makeConfig: "{x}N1,N2...N9" into args (libzpaq.cpp:6893-6913) ----
-  const char* m = ms.c_str();
-  int args[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  ++m;
-  for (int i = 0; i < 9 && (isdigit((unsigned char)*m) || *m == ',' || *m == '.');) {
-    if (isdigit((unsigned char)*m)) args[i] = args[i] * 10 + *m - '0';
-    else if (++i < 9) args[i] = 0;
-    ++m;
+  else if (ms[0] == 'x') {
+    // "x" N1 [, N2 ...]: block size class, pre-processing type (must be 0 here), further arguments of the pre-processor;
+    // up to nine numbers, then the component tokens (libzpaq.cpp:6893-6913)
+    const char* s = ms.c_str() + 1;
+    int head[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k = 0;
+    for (; k < 9 && (isdigit((unsigned char)*s) || *s == ',' || *s == '.'); ++s) {
+      if (isdigit((unsigned char)*s)) head[k] = head[k] * 10 + (*s - '0');
+      else if (++k < 9) head[k] = 0;
+    }
+    size_class = head[0]; preprocessing = head[1];
+    tokens = tokenize(s);
   }
-  if (args[1] != 0) { *err = "pre-processing (LZ77/BWT/E8E9) is outside the context-mixing path"; return ZPQ_E_METHOD; }
-  if ((0x100000ull << args[0]) - 4096 < n && args[0] < 11) { /* the reference only asserts this */ }
-  if (args[0] > 11) { *err = "block size argument too big"; return ZPQ_E_METHOD; }
+  else { *err = "Unsupported method"; return ZPQ_E_METHOD; }
+  if (preprocessing != 0) { *err = "pre-processing (LZ77/BWT/E8E9) is outside the context-mixing path"; return ZPQ_E_METHOD; }
+  if (size_class > 11) { *err = "block size argument too big"; return ZPQ_E_METHOD; }
 
-  // ---- context model section (libzpaq.cpp:7325-7534) ----
-  int ncomp = 0;
-  const int membits = args[0] + 20;
-  int sb = 5;
-  Comp comp;
-  Asm h;
-  h.op(C_DEC); h.op(PC_A); h.op(ADD_N, 255); h.op(D_A); h.op(PD_C);   // c-- *c=a a+= 255 d=a *d=c
-
-  while (*m && ncomp < 254) {
-    std::vector<int> v;
-    v.push_back((unsigned char)*m++);
-    if (isdigit((unsigned char)*m)) {
-      v.push_back(*m++ - '0');
-      while (isdigit((unsigned char)*m) || *m == ',' || *m == '.') {
-        if (isdigit((unsigned char)*m)) v.back() = v.back() * 10 + *m++ - '0';
-        else { v.push_back(0); ++m; }
-      }
-    }
-
-    if (v[0] == 'c') {   // context model: ICM or CM with optional special/masked contexts
-      while (v.size() < 3) v.push_back(0);
-      sb = 11;
-      if (v[2] < 256) sb += lg((unsigned)v[2]); else sb += 6;
-      for (size_t i = 3; i < v.size(); ++i) if (v[i] < 512) sb += popcount((unsigned)v[i]) * 3 / 4;
-      if (sb > membits) sb = membits;
-      if (v[1] % 1000 == 0) comp.add(ZT_ICM, sb - 6 - v[1] / 1000);
-      else comp.add(ZT_CM, sb - 2 - v[1] / 1000, v[1] % 1000 - 1);
-      h.op(D_N, ncomp); h.op(PD_ZERO);
-      if (v[2] > 1 && v[2] <= 255) {   // periodic context
-        h.op(A_C);
-        if (lg((unsigned)v[2]) != lg((unsigned)v[2] - 1)) h.op(AND_N, v[2] - 1);
-        else h.op(MOD_N, v[2]);
-        h.op(HASHD);
-      }
-      else if (v[2] >= 1000 && v[2] <= 1255) {   // distance to last occurrence
-        h.op(A_N, 255); h.op(ADD_N, v[2] - 1000); h.op(D_A); h.op(A_PD); h.op(SUB_C);
-        h.op(GT_N, 255); h.if_(); h.op(A_N, 255); h.endif_();
-        h.op(D_N, ncomp); h.op(HASHD);
-      }
-      for (size_t i = 3; i < v.size(); ++i) {   // masked context bytes
-        if (i == 3) h.op(B_C);
-        if (v[i] == 255) { h.op(A_PB); h.op(HASHD); }
-        else if (v[i] > 0 && v[i] < 255) { h.op(A_PB); h.op(AND_N, v[i]); h.op(HASHD); }
-        else if (v[i] >= 256 && v[i] < 512) {   // lz77 parse state or masked literal
-          h.op(A_R, 1); h.op(GT_N, 1); h.if_();
-            h.op(A_R, 2); h.op(LT_N, 64); h.if_();
-              h.op(A_PB);
-              if (v[i] < 511) h.op(AND_N, v[i] - 256);
-              h.op(HASHD);
-            h.else_();
-              h.op(SHR_N, 6); h.op(HASHD); h.op(A_R, 1); h.op(HASHD);
-            h.endif_();
-          h.else_();
-            h.op(A_N, 255); h.op(HASHD); h.op(A_R, 2); h.op(HASHD);
-          h.endif_();
-        }
-        else if (v[i] >= 1256) {
-          h.op(A_N, ((v[i] - 1000) >> 8) & 255); h.op(SHL_N, 8); h.op(ADD_N, (v[i] - 1000) & 255);
-          h.op(ADD_B); h.op(B_A);
-        }
-        else if (v[i] > 1000) { h.op(A_N, v[i] - 1000); h.op(ADD_B); h.op(B_A); }
-        if (v[i] < 512 && i < v.size() - 1) h.op(B_INC);
-      }
-      ++ncomp;
-    }
-
-    if (strchr("mts", v[0]) && ncomp > (v[0] == 't')) {   // MIX, MIX2, SSE
-      if (v.size() <= 1) v.push_back(8);
-      if (v.size() <= 2) v.push_back(24 + 8 * (v[0] == 's'));
-      if (v[0] == 's' && v.size() <= 3) v.push_back(255);
-      sb = 5 + v[1] * 3 / 4;
-      if (v[0] == 'm') comp.add(ZT_MIX, v[1], 0, ncomp, v[2], 255);
-      else if (v[0] == 't') comp.add(ZT_MIX2, v[1], ncomp - 1, ncomp - 2, v[2], 255);
-      else comp.add(ZT_SSE, v[1], ncomp - 1, v[2], v[3]);
-      if (v[1] > 8) {
-        h.op(D_N, ncomp); h.op(PD_ZERO); h.op(B_C); h.op(A_ZERO);
-        for (; v[1] >= 16; v[1] -= 8) {
-          h.op(SHL_N, 8); h.op(ADD_PB);
-          if (v[1] > 16) h.op(B_INC);
-        }
-        if (v[1] > 8) { h.op(SHL_N, 8); h.op(ADD_PB); h.op(SHR_N, 16 - v[1]); }
-        h.op(SHL_N, 8); h.op(PD_A);
-      }
-      ++ncomp;
-    }
-
-    if (v[0] == 'i' && ncomp > 0) {   // ISSE chain
-      h.op(D_N, ncomp - 1); h.op(B_C); h.op(A_PD); h.op(D_INC);
-      for (size_t i = 1; i < v.size() && ncomp < 254; ++i) {
-        for (int j = 0; j < v[i] % 10; ++j) {
-          h.op(HASH);
-          if (i < v.size() - 1 || j < v[i] % 10 - 1) h.op(B_INC);
-          sb += 6;
-        }
-        h.op(PD_A);
-        if (i < v.size() - 1) h.op(D_INC);
-        if (sb > membits) sb = membits;
-        comp.add(ZT_ISSE, sb - 6 - v[i] / 10, ncomp - 1);
-        ++ncomp;
-      }
-    }
-
-    if (v[0] == 'a') {   // MATCH
-      if (v.size() <= 1) v.push_back(24);
-      while (v.size() < 4) v.push_back(0);
-      comp.add(ZT_MATCH, membits - v[3] - 2, membits - v[2]);
-      h.op(D_N, ncomp); h.op(A_PD); h.op(MUL_N, v[1]); h.op(ADD_PC); h.op(A_INC); h.op(PD_A);
-      sb = 5 + (membits - v[2]) * 3 / 4;
-      ++ncomp;
-    }
-
-    if (v[0] == 'w') {   // word-model ICM-ISSE chain
-      if (v.size() <= 1) v.push_back(1);
-      if (v.size() <= 2) v.push_back(65);
-      if (v.size() <= 3) v.push_back(26);
-      if (v.size() <= 4) v.push_back(223);
-      if (v.size() <= 5) v.push_back(20);
-      if (v.size() <= 6) v.push_back(0);
-      comp.add(ZT_ICM, membits - 6 - v[6]);
-      for (int i = 1; i < v[1]; ++i) comp.add(ZT_ISSE, membits - 6 - v[6], ncomp + i - 1);
-      h.op(A_PC); h.op(AND_N, v[4]); h.op(SUB_N, v[2]); h.op(AND_N, 255); h.op(LT_N, v[3]); h.if_();
-      for (int i = 0; i < v[1]; ++i) {
-        if (i == 0) h.op(D_N, ncomp); else h.op(D_INC);
-        h.op(A_PD); h.op(MUL_N, v[5]); h.op(ADD_PC); h.op(A_INC); h.op(PD_A);
-      }
-      h.else_();
-      for (int i = v[1] - 1; i > 0; --i) { h.op(D_N, ncomp + i - 1); h.op(A_PD); h.op(D_INC); h.op(PD_A); }
-      h.op(D_N, ncomp); h.op(PD_ZERO);
-      h.endif_();
-      ncomp += v[1] - 1;
-      sb = membits - v[6];
-      ++ncomp;
-    }
+  Draft d;
+  d.membits = size_class + 20;
+  d.emit(kProlog);
+  for (const Token& t : tokens) {
+    if (d.count() >= 254) break;
+    for (const Family& f : kFamilies) if (f.letter == t.letter) { f.build(d, t); break; }
   }
-  h.op(HALT);
-  if (!h.ok || !comp.ok || !h.ifs.empty() || ncomp > 255) { *err = "method arguments out of range"; return ZPQ_E_METHOD; }
-
-  // header: hsize[2] hh hm ph pm n COMP 0 HCOMP 0   ("comp 9 16 0 0", libzpaq.cpp:7307)
-  const size_t hsize = 5 + comp.b.size() + 1 + h.b.size() + 1;
-  if (hsize > 65535) { *err = "program too big"; return ZPQ_E_METHOD; }
-  hdr->clear();
-  hdr->push_back((uint8_t)(hsize & 255)); hdr->push_back((uint8_t)(hsize >> 8));
-  hdr->push_back(9); hdr->push_back(16); hdr->push_back(0); hdr->push_back(0);
-  hdr->push_back((uint8_t)ncomp);
-  hdr->insert(hdr->end(), comp.b.begin(), comp.b.end());
-  hdr->push_back(0);
-  hdr->insert(hdr->end(), h.b.begin(), h.b.end());
-  hdr->push_back(0);
-  return ZPQ_OK;
+  one(d, HALT);
+  if (!d.ok || !d.open_jumps.empty() || d.count() > 255) { *err = "method arguments out of range"; return ZPQ_E_METHOD; }
+  return serialise(d, hdr, err);
 }
 
 }  // namespace zpq

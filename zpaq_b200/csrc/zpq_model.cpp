@@ -364,7 +364,7 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
   build_recipes(M, hdr + pos, prog_len);
   if (M->rcp.ok) for (uint32_t l = 0; l < M->n; ++l) if (M->rcp.len[l] > ZPQ_FAST_RCP) M->fast.ok = 0;
 
-  // ================= skewed-pipeline encode plan (zpq_kernels3.cu) =================
+  // ================= skewed-pipeline encode plan (depths used by the wavefront encoder) =================
   {
     ZPipe& P = M->pipe;
     memset(&P, 0, sizeof(P));
@@ -428,7 +428,7 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
     P.dmax = dmax; P.nsp = nsp; P.ok = ok ? 1 : 0;
   }
 
-  // ================= three-warp team plan (zpq_kernels4.cu) =================
+  // ================= three-warp team plan (mixer list used by the wavefront encoder) =================
   {
     ZTeam& T = M->team;
     memset(&T, 0, sizeof(T));
