@@ -315,6 +315,96 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_sharded(args, rank, local_rank, world, dist):
+    """north_star's multi-GPU data path, measured: rank 0 holds every raw block in pinned host memory; per step they go up
+    to its HBM, are scattered over NCCL, coded where they land (zpq_compress_blocks_dev), gathered and copied down; the
+    archive then takes the same way for decompression.  One process per GPU; with --gpus 1 the collectives are no-ops."""
+    import torch
+    import zpaq_b200 as Z
+    from zpaq_b200 import shard
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from sharded_roundtrip import gen_blocks_tensor
+    if dist is None:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+    cfg = args.config
+    METHOD, ref_method, total, KIND, label = CONFIGS[cfg]
+    per_gpu = args.blocks or (total + BLOCK - 1) // BLOCK
+    nblk = per_gpu * world
+    dev = torch.device("cuda", local_rank)
+    ctx = Z.Context(local_rank)
+
+    def sync():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    host = host_arc = host_out = None
+    lens = None
+    if rank == 0:
+        host = gen_blocks_tensor(nblk, BLOCK, kind=KIND, seed=SEED)
+        lens = [BLOCK] * nblk
+        host_arc = torch.empty(nblk * (BLOCK // 2 + BLOCK // 8 + 80000), dtype=torch.uint8, pin_memory=True)
+        host_out = torch.empty(nblk * BLOCK, dtype=torch.uint8, pin_memory=True)
+
+    def step(nb):
+        """one round trip over the first nb blocks; returns phase times"""
+        t0 = time.perf_counter()
+        flat = host[:nb * BLOCK].to(dev, non_blocking=True) if rank == 0 else None
+        arc, alens, tc = shard.compress_sharded(ctx, METHOD, flat, lens[:nb] if rank == 0 else None, src=0, device=dev, sync=sync)
+        if rank == 0:
+            host_arc[:arc.numel()].copy_(arc, non_blocking=True)
+        sync(); t1 = time.perf_counter()
+        arc2 = host_arc[:arc.numel()].to(dev, non_blocking=True) if rank == 0 else None
+        out, olens, td = shard.decompress_sharded(ctx, arc2, src=0, device=dev, sync=sync)
+        if rank == 0:
+            host_out[:out.numel()].copy_(out, non_blocking=True)
+        sync(); t2 = time.perf_counter()
+        return {"wall_c": t1 - t0, "wall_d": t2 - t1, "dev_c": tc["dev_s"], "dev_d": td["dev_s"], "scatter_c": tc["scatter_s"], "gather_c": tc["gather_s"],
+                "scatter_d": td["scatter_s"], "gather_d": td["gather_s"], "arc": int(arc.numel()) if rank == 0 else 0}
+
+    for w in range(args.warmup):
+        r = step(nblk if w == 0 else max(world, nblk // 8))
+    if rank == 0 and args.warmup and not bool(torch.equal(host, host_out)):
+        raise SystemExit("sharded round trip mismatch")
+    acc = {}
+    done = 0
+    sync(); t_begin = time.perf_counter()
+    for k in range(args.steps):
+        if done >= 1:
+            over = torch.tensor([1.0 if (time.time() - T_START) + 1.2 * r["wall_c"] + 1.2 * r["wall_d"] + 30 > BUDGET_S else 0.0], device=dev)
+            dist.all_reduce(over, op=dist.ReduceOp.MAX)
+            if over.item() > 0:
+                break
+        r = step(nblk)
+        done += 1
+        for key, v in r.items():
+            acc[key] = acc.get(key, 0.0) + v
+    sync(); wall = time.perf_counter() - t_begin
+    t = torch.tensor([acc["dev_c"], acc["dev_d"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_c, dev_d = float(t[0]), float(t[1])
+    if rank == 0:
+        if not bool(torch.equal(host, host_out)):
+            raise SystemExit("sharded round trip mismatch")
+        mb = nblk * BLOCK * done / 1e6
+        line = {"metric": metric_name(cfg), "mode": "sharded", "value": mb / (dev_c + dev_d), "unit": "MB/s", "n_gpus": world, "steps": done,
+                "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, done), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": "%s; sharded data path: rank 0 holds %d blocks x %d B, NCCL scatter of raw blocks / gather of coded blocks"
+                                       % (label, nblk, BLOCK), "blocks_per_gpu": per_gpu, "block_bytes": BLOCK, "method": METHOD,
+                           "parallelism": "block-shard x%d; NCCL point-to-point scatter / gather around the coding path" % world},
+                "compress_MBps": mb / dev_c, "decompress_MBps": mb / dev_d,
+                "e2e": {"value": mb / (acc["wall_c"] + acc["wall_d"]), "unit": "MB/s", "compress_MBps": mb / acc["wall_c"], "decompress_MBps": mb / acc["wall_d"],
+                        "h2d_bytes_per_step": int(nblk * BLOCK + acc["arc"] / done), "d2h_bytes_per_step": int(nblk * BLOCK + acc["arc"] / done)},
+                "nccl": {"scatter_raw_s": acc["scatter_c"] / done, "gather_coded_s": acc["gather_c"] / done, "scatter_coded_s": acc["scatter_d"] / done,
+                         "gather_raw_s": acc["gather_d"] / done, "scatter_raw_GBps": nblk * BLOCK / 1e9 / max(acc["scatter_c"] / done, 1e-9)},
+                "total_s": time.time() - T_START}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -324,6 +414,9 @@ def main():
     ap.add_argument("--config", default="m5_1g", choices=sorted(CONFIGS))
     ap.add_argument("--blocks", type=int, default=0, help="blocks per GPU (default: the configuration's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="local", choices=["local", "sharded"],
+                    help="local (default, the contract line): every rank codes its own data; sharded: rank 0 holds all blocks, "
+                         "NCCL scatters raw blocks / gathers coded blocks (north_star's data path), not the headline line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -349,6 +442,9 @@ def main():
 
     cfg = args.config
     METHOD, ref_method, total, KIND, label = CONFIGS[cfg]
+    if args.mode == "sharded":
+        run_sharded(args, rank, local_rank, world, dist)
+        return
     nblk = args.blocks or (total + BLOCK - 1) // BLOCK
     sizes = [BLOCK] * nblk
     if not args.blocks and total % BLOCK:

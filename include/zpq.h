@@ -143,6 +143,33 @@ int zpq_compress_blocks(zpq_ctx* ctx, int nblk, const char* method,
                         const char* const* filenames, const char* const* comments, int dosha1,
                         uint8_t* const* out, const uint64_t* out_cap, uint64_t* out_len,
                         int32_t* status);
+/* The same with payloads and output blocks in HBM (block sharding: raw blocks arrive over NCCL, coded blocks leave the
+ * same way).  data[i] / out[i] are device pointers; every other argument is host memory.  SHA-1 (libzpaq.cpp:101-177) and
+ * the level-5 payload statistics (libzpaq.cpp:7655-7688) are computed on the device as well, so the host never reads the
+ * payload bytes. */
+int zpq_compress_blocks_dev(zpq_ctx* ctx, int nblk, const char* method,
+                            const uint8_t* const* d_data, const uint64_t* len,
+                            const char* const* filenames, const char* const* comments, int dosha1,
+                            uint8_t* const* d_out, const uint64_t* out_cap, uint64_t* out_len,
+                            int32_t* status);
+/* zpq_model_from_method with the payload statistics already taken (zpq_analyze_dev): gaps[2] as returned there. */
+int zpq_header_from_stats(const char* method, uint64_t n, const int32_t gaps[2], uint8_t* hdr, int cap, int* hlen);
+/* Device-side analysis of payloads in HBM: sha1 = 20 bytes per block (or NULL), gaps = 2 ints per block (the dominant
+ * byte-gap periods level 5 models, 0 = none; or NULL).  Results are host arrays. */
+int zpq_analyze_dev(zpq_ctx* ctx, int nblk, const uint8_t* const* d_data, const uint64_t* len,
+                    uint8_t* sha1, int32_t* gaps);
+/* Framing scan of an in-memory archive (Decompresser::findBlock / findFilename / readComment / readSegmentEnd and
+ * Decoder::skip, libzpaq.cpp:2158-2181, 2247-2373): one record per segment, for callers that shard blocks themselves
+ * and decode with zpq_decode_blocks[_dev].  No device is involved.  coded_len includes the terminating zeros. */
+typedef struct zpq_segment {
+  uint32_t block, segment;      /* block index in the archive, segment index in the block */
+  uint64_t hdr_off;             /* block header (hsize[2] ... HCOMP END) */
+  uint32_t hlen, components;    /* header bytes; number of components (0 = stored block) */
+  uint64_t coded_off, coded_len;
+  int64_t size_hint;            /* decimal prefix of the segment comment (what compressBlock writes), -1 if none */
+  int32_t has_sha1; uint8_t sha1[20];
+} zpq_segment;
+int zpq_scan_archive(const uint8_t* arc, uint64_t arc_len, zpq_segment* segs, int cap, int* nsegs, int* nblocks);
 /* Batched libzpaq::decompress (libzpaq.cpp:2376-2389) over one in-memory
  * archive: finds every block (Decompresser::findBlock, libzpaq.cpp:2247),
  * decodes all modelled blocks concurrently on the GPU, post-processes on the

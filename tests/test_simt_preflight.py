@@ -31,6 +31,16 @@ def test_production_kernels_on_the_emulator(simt_build):
     assert r.returncode == 0 and "simt preflight ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+@pytest.mark.timeout(900)
+def test_sharded_data_path_two_ranks_gloo(simt_build):
+    """zpaq_b200.shard.compress_sharded / decompress_sharded over gloo, world size 2: scatter of raw blocks as tensors, the
+    device-resident whole-block entry point (SHA-1 and level-5 statistics on the "device"), gather of coded blocks; the
+    archive must equal the unmodified reference's block by block and decode back to the input."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt_shard_case.py"), simt_build],
+                       capture_output=True, text=True, timeout=800, env=dict(os.environ, SIMT_WATCHDOG="600"))
+    assert r.returncode == 0 and "simt shard ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 @pytest.mark.timeout(600)
 def test_emulator_selftest():
     """The emulator's own semantics (shuffles, ballots, reductions, barriers, named barriers, spin hand-shakes between

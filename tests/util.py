@@ -39,3 +39,38 @@ def split_segments(d, nseg):
         segs.append(d[pos:pos + ln])
         pos += ln
     return segs
+
+
+class DevBytes:
+    """Bytes in device memory for the *_dev entry points: a torch CUDA tensor on a GPU box; on the SIMT emulator (tools/simt,
+    where "device" memory is host memory) a ctypes buffer."""
+
+    def __init__(self, data=None, size=None):
+        import ctypes as C
+        n = len(data) if data is not None else size
+        self.n = n
+        try:
+            import torch
+            cuda = torch.cuda.is_available()
+        except Exception:
+            cuda = False
+        if cuda:
+            import torch
+            if data is not None:
+                self.t = torch.frombuffer(bytearray(bytes(data) + b"\0" * 16), dtype=torch.uint8).cuda()
+            else:
+                self.t = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            self.ptr = self.t.data_ptr()
+        else:
+            self.t = None
+            self.buf = C.create_string_buffer(bytes(data) + b"\0" * 16 if data is not None else n + 16)
+            self.ptr = C.cast(self.buf, C.c_void_p).value
+
+    def bytes(self, n=None):
+        n = self.n if n is None else n
+        if self.t is not None:
+            import torch
+            torch.cuda.synchronize()
+            return bytes(self.t[:n].cpu().numpy().tobytes())
+        return self.buf.raw[:n]

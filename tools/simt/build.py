@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "zpaq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
-CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_abi.cu"]
+CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_prep.cu", "zpq_abi.cu"]
 CPP = ["zpq_model.cpp", "zpq_method.cpp", "zpq_frame.cpp", "zpq_hcomp.cpp"]
 
 
@@ -94,7 +94,8 @@ def main():
     if bad:
         raise SystemExit("compile failed: " + " ".join(bad[0]))
     lib = os.path.join(OUT, "libzpq_simt.so")
-    subprocess.check_call(["g++", "-shared", "-o", lib + ".new"] + objs + ["-lpthread"])
+    # -Bsymbolic: the library's calls to its own cuda* emulation must not be interposed by a real libcudart that torch loaded first
+    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", lib + ".new"] + objs + ["-lpthread"])
     os.replace(lib + ".new", lib)          # a process that has the old build loaded keeps its mapping
     print("built", lib)
     # the unchanged zpaq.cpp + the shim, linked against the emulator build instead of the CUDA build (objects from `make -C oracle cli`)

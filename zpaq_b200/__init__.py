@@ -28,6 +28,28 @@ class ZpqError(RuntimeError):
         self.rc = rc
 
 
+class Segment(C.Structure):
+    """zpq_segment (include/zpq.h): one segment of an archive as zpq_scan_archive reports it."""
+    _fields_ = [("block", C.c_uint32), ("segment", C.c_uint32), ("hdr_off", C.c_uint64), ("hlen", C.c_uint32),
+                ("components", C.c_uint32), ("coded_off", C.c_uint64), ("coded_len", C.c_uint64), ("size_hint", C.c_int64),
+                ("has_sha1", C.c_int32), ("sha1", C.c_uint8 * 20)]
+
+
+def scan_archive(arc):
+    """[Segment] of an in-memory archive (host only, no device)."""
+    arc = bytes(arc)
+    n = C.c_int(0); nb = C.c_int(0)
+    buf = C.create_string_buffer(arc, max(len(arc), 1))
+    rc = lib().zpq_scan_archive(C.cast(buf, C.c_void_p), len(arc), None, 0, C.byref(n), C.byref(nb))
+    if rc:
+        raise ZpqError(rc)
+    segs = (Segment * max(n.value, 1))()
+    rc = lib().zpq_scan_archive(C.cast(buf, C.c_void_p), len(arc), C.cast(segs, C.c_void_p), n.value, C.byref(n), C.byref(nb))
+    if rc:
+        raise ZpqError(rc)
+    return list(segs[:n.value])
+
+
 class Job(C.Structure):
     _fields_ = [("hdr", C.c_void_p), ("hlen", C.c_int32), ("nseg", C.c_int32),
                 ("data", C.c_void_p), ("len", C.c_uint64), ("seg_len", C.c_void_p),
@@ -39,7 +61,8 @@ EXPORTS = ["zpq_abi_version", "zpq_create", "zpq_destroy", "zpq_strerror", "zpq_
            "zpq_set_workspace", "zpq_set_stream", "zpq_model_bytes", "zpq_model_from_method",
            "zpq_encode_blocks", "zpq_decode_blocks", "zpq_encode_blocks_dev", "zpq_decode_blocks_dev",
            "zpq_last_timing", "zpq_launch_count", "zpq_compress_blocks", "zpq_decompress_archive",
-           "zpq_compress_bound", "zpq_postprocess_block", "zpq_model_describe", "zpq_last_tiers"]
+           "zpq_compress_bound", "zpq_postprocess_block", "zpq_model_describe", "zpq_last_tiers",
+           "zpq_compress_blocks_dev", "zpq_analyze_dev", "zpq_scan_archive", "zpq_header_from_stats"]
 
 _lib = None
 
@@ -72,6 +95,9 @@ def lib():
         L.zpq_last_tiers.argtypes = [vp, C.POINTER(C.c_uint32)]
         L.zpq_launch_count.restype = u64
         L.zpq_compress_blocks.argtypes = [vp, i32, C.c_char_p, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+        L.zpq_compress_blocks_dev.argtypes = [vp, i32, C.c_char_p, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+        L.zpq_analyze_dev.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.zpq_scan_archive.argtypes = [vp, u64, vp, i32, C.POINTER(i32), C.POINTER(i32)]
         L.zpq_decompress_archive.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(i32), i32]
         L.zpq_compress_bound.argtypes = [u64]
         L.zpq_postprocess_block.argtypes = [C.c_char_p, i32, vp, vp, i32, vp, u64, C.POINTER(u64), vp]
@@ -242,6 +268,56 @@ class Context:
         if rc:
             raise ZpqError(rc, self.last_error())
         return [outs[i].raw[:olen[i]] for i in range(n)]
+
+    # -- device-resident (callers pass raw device pointers, e.g. torch tensors' data_ptr()) ------------------------------
+    def analyze_dev(self, ptrs, lens, sha1=True, gaps=True):
+        """(list of 20-byte digests or None, list of (gap0, gap1) or None) for payloads in HBM."""
+        n = len(ptrs)
+        pa = (C.c_void_p * n)(*ptrs)
+        la = (C.c_uint64 * n)(*lens)
+        sb = (C.c_uint8 * (20 * n))() if sha1 else None
+        gb = (C.c_int32 * (2 * n))() if gaps else None
+        rc = lib().zpq_analyze_dev(self._h, n, C.cast(pa, C.c_void_p), C.cast(la, C.c_void_p),
+                                   C.cast(sb, C.c_void_p) if sha1 else None, C.cast(gb, C.c_void_p) if gaps else None)
+        if rc:
+            raise ZpqError(rc, self.last_error())
+        return ([bytes(sb[20 * i:20 * i + 20]) for i in range(n)] if sha1 else None,
+                [(gb[2 * i], gb[2 * i + 1]) for i in range(n)] if gaps else None)
+
+    def decode_blocks_dev(self, hdrs, ptrs, lens, out_ptrs, out_caps, seg_lens=None):
+        """zpq_decode_blocks_dev: coded segments (each with its terminator zeros) and outputs in HBM.
+        Returns [(status, out_len, [segment output lengths])]."""
+        n = len(ptrs)
+        jobs = (Job * n)()
+        keep = []
+        for i in range(n):
+            h = C.create_string_buffer(bytes(hdrs[i]), len(hdrs[i]))
+            sl = seg_lens[i] if seg_lens and seg_lens[i] else [lens[i]]
+            sa = (C.c_uint64 * len(sl))(*sl)
+            so = (C.c_uint64 * len(sl))()
+            keep.append((h, sa, so))
+            jobs[i].hdr = _addr(h); jobs[i].hlen = len(hdrs[i]); jobs[i].nseg = len(sl)
+            jobs[i].data = ptrs[i]; jobs[i].len = lens[i]; jobs[i].seg_len = _addr(sa)
+            jobs[i].out = out_ptrs[i]; jobs[i].out_cap = out_caps[i]; jobs[i].seg_out = _addr(so)
+        rc = lib().zpq_decode_blocks_dev(self._h, n, jobs)
+        if rc:
+            raise ZpqError(rc, self.last_error())
+        return [(jobs[i].status, int(jobs[i].out_len), list(keep[i][2])) for i in range(n)]
+
+    def compress_blocks_dev(self, method, ptrs, lens, out_ptrs, out_caps, dosha1=True):
+        """zpq_compress_blocks_dev: payloads and output blocks in HBM; returns (status list, block length list)."""
+        n = len(ptrs)
+        pa = (C.c_void_p * n)(*ptrs)
+        la = (C.c_uint64 * n)(*lens)
+        oa = (C.c_void_p * n)(*out_ptrs)
+        ca = (C.c_uint64 * n)(*out_caps)
+        ol = (C.c_uint64 * n)()
+        st = (C.c_int32 * n)()
+        rc = lib().zpq_compress_blocks_dev(self._h, n, method.encode(), C.cast(pa, C.c_void_p), C.cast(la, C.c_void_p), None, None,
+                                           int(dosha1), C.cast(oa, C.c_void_p), C.cast(ca, C.c_void_p), C.cast(ol, C.c_void_p), C.cast(st, C.c_void_p))
+        if rc:
+            raise ZpqError(rc, self.last_error())
+        return list(st), list(ol)
 
     def decompress_archive(self, arc, cap, verify=True):
         arc = bytes(arc)

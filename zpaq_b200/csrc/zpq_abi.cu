@@ -59,10 +59,11 @@ struct zpq_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   ZTables* d_tables = nullptr;
   void* ws = nullptr; uint64_t ws_bytes = 0; bool own_ws = true;
-  DevBuf d_in, d_out, d_meta, d_pbuf, d_cstate;
+  DevBuf d_in, d_out, d_meta, d_pbuf, d_cstate, d_prep, d_stage_in, d_stage_out;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   float ms[3] = {0, 0, 0};
+  float ms_prep = 0;           // device time of the last analysis pass (SHA-1, gap statistics); added to ms[0] by the whole-block calls
   uint64_t launches = 0;
   uint32_t tiers[6] = {0, 0, 0, 0, 0, 0};   // blocks of the last batch per kernel tier (zpq_last_tiers)
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
@@ -144,7 +145,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot), "cudaMemGetInfo");
     const uint64_t avail = (uint64_t)fr + ctx->ws_bytes;
-    const uint64_t reserve = ((uint64_t)3 << 30) + ((!decode && ctx->kernel_version >= 5) ? ((uint64_t)14 << 30) : 0);   // staging, CUDA context, prediction streams
+    const uint64_t reserve = ((uint64_t)8 << 30) + ((!decode && ctx->kernel_version >= 5) ? ((uint64_t)14 << 30) : 0);   // staging, CUDA context, prediction streams
     uint64_t want = std::min(need_all, avail > reserve ? avail - reserve : 0);
     if (want > ctx->ws_bytes) {
       if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
@@ -248,7 +249,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
         IJob& J = jobs[wave[k]];
         uint64_t at = blocks[k].in_off;
         for (const Piece& pc : J.in) {
-          if (pc.n) CK(cudaMemcpyAsync((uint8_t*)ctx->d_in.p + at, pc.p, pc.n, cudaMemcpyHostToDevice, st), "H2D input");
+          if (pc.n) CK(cudaMemcpyAsync((uint8_t*)ctx->d_in.p + at, pc.p, pc.n, cudaMemcpyDefault, st), "input staging");      // a piece may be host or device memory
           at += pc.n;
         }
       }
@@ -415,7 +416,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           J.first_byte = fb;
         }
         if (have > J.out_skip && J.out)
-          CK(cudaMemcpyAsync(J.out, src + J.out_skip, have - J.out_skip, cudaMemcpyDeviceToHost, st), "D2H output");
+          CK(cudaMemcpyAsync(J.out, src + J.out_skip, have - J.out_skip, cudaMemcpyDefault, st), "output copy");          // host or device destination
       }
     }
     CK(cudaStreamSynchronize(st), "stream sync");
@@ -522,7 +523,7 @@ void zpq_destroy(zpq_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release();
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release(); ctx->d_prep.release(); ctx->d_stage_in.release(); ctx->d_stage_out.release();
   if (ctx->own_ws && ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -584,6 +585,18 @@ int zpq_model_from_method(const char* method, const uint8_t* data, uint64_t n, u
   return ZPQ_OK;
 }
 
+int zpq_header_from_stats(const char* method, uint64_t n, const int32_t gaps[2], uint8_t* hdr, int cap, int* hlen) {
+  if (!method || !hdr || !hlen) return ZPQ_E_ARG;
+  std::vector<uint8_t> h; std::string e;
+  const int g[2] = {gaps ? gaps[0] : 0, gaps ? gaps[1] : 0};
+  const int rc = header_from_stats(method, n, g, &h, &e);
+  if (rc != ZPQ_OK) return rc;
+  if ((int)h.size() > cap) return ZPQ_E_OUTPUT_FULL;
+  memcpy(hdr, h.data(), h.size());
+  *hlen = (int)h.size();
+  return ZPQ_OK;
+}
+
 int zpq_encode_blocks(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, false, false); }
 int zpq_decode_blocks(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, true, false); }
 int zpq_encode_blocks_dev(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, false, true); }
@@ -618,74 +631,211 @@ int zpq_postprocess_block(const uint8_t* hdr, int hlen, const uint8_t* model_out
 
 uint64_t zpq_compress_bound(uint64_t len) { return len + len / 8 + 1024; }
 
-// Batched libzpaq::compressBlock (libzpaq.cpp:7543-7731), context-model family only.
-int zpq_compress_blocks(zpq_ctx* ctx, int nblk, const char* method, const uint8_t* const* data,
-                        const uint64_t* len, const char* const* filenames, const char* const* comments,
-                        int dosha1, uint8_t* const* out, const uint64_t* out_cap, uint64_t* out_len,
-                        int32_t* status) {
-  if (!ctx || nblk < 0 || !method || (nblk && (!data || !len || !out || !out_cap || !out_len))) return ZPQ_E_ARG;
-  static const uint8_t kPass = 0;   // post-processor flag PASS goes through the model first (libzpaq.cpp:2914)
-  std::vector<std::vector<uint8_t>> hdrs(nblk), pro(nblk);
-  std::vector<std::vector<uint8_t>> sha(nblk);
-  std::vector<int> st(nblk, ZPQ_OK);
-  // host-side per-block work (model selection incl. the level-5 scan, SHA-1) on all host threads
-  {
-    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
-    nt = std::min<unsigned>(nt, (unsigned)std::max(1, nblk));
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t)
-      th.emplace_back([&, t]() {
-        for (int i = (int)t; i < nblk; i += (int)nt) {
-          std::string e;
-          if (len[i] > 0x7fffffffull - 4096) { st[i] = ZPQ_E_ARG; continue; }
-          st[i] = header_from_method(method, data[i], len[i], &hdrs[i], &e);
-          if (st[i] != ZPQ_OK) continue;
-          char cs[32];
-          snprintf(cs, sizeof(cs), "%llu", (unsigned long long)len[i]);
-          std::string comment = cs;                                   // libzpaq.cpp:7702-7703
-          if (comments && comments[i]) { comment += " "; comment += comments[i]; }
-          write_block_prologue(&pro[i], hdrs[i].data(), (int)hdrs[i].size(),
-                               filenames ? filenames[i] : nullptr, comment.c_str());
-          if (dosha1) { sha[i].resize(20); sha1_of(data[i], len[i], sha[i].data()); }
-        }
-      });
-    for (auto& t : th) t.join();
+static int64_t comment_size_hint(const uint8_t* arc, const SegmentView& s);
+
+// Device-side analysis of block payloads that are already in HBM: SHA-1 and the level-5 gap statistics (zpq_prep.cu).
+// sha1 (20 bytes per block) and gaps (2 ints per block) are host arrays; either may be null.
+static int analyze_dev(zpq_ctx* ctx, int nblk, const uint8_t* const* d_data, const uint64_t* len, uint8_t* sha1, int32_t* gaps) {
+  if (nblk <= 0 || (!sha1 && !gaps)) return ZPQ_OK;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t st = ctx->stream;
+  const uint64_t o_ptr = 0, o_len = align_up((uint64_t)nblk * 8, 256), o_sha = o_len + align_up((uint64_t)nblk * 8, 256),
+                 o_gap = o_sha + align_up((uint64_t)nblk * 20, 256), total = o_gap + align_up((uint64_t)nblk * 8, 256);
+  CK(ctx->d_prep.reserve(total), "analysis cudaMalloc");
+  uint8_t* dp = (uint8_t*)ctx->d_prep.p;
+  CK(cudaMemcpyAsync(dp + o_ptr, d_data, (size_t)nblk * 8, cudaMemcpyHostToDevice, st), "H2D pointers");
+  CK(cudaMemcpyAsync(dp + o_len, len, (size_t)nblk * 8, cudaMemcpyHostToDevice, st), "H2D lengths");
+  CK(cudaEventRecord(ctx->ev[0], st), "event");
+  if (sha1) {
+    CK(zpq_launch_sha1((const uint8_t* const*)(dp + o_ptr), (const uint64_t*)(dp + o_len), dp + o_sha, nblk, st), "zpq_sha1_kernel launch");
+    CK(cudaMemcpyAsync(sha1, dp + o_sha, (size_t)nblk * 20, cudaMemcpyDeviceToHost, st), "D2H sha1");
+    ++ctx->launches;
   }
+  if (gaps) {
+    CK(zpq_launch_gaps((const uint8_t* const*)(dp + o_ptr), (const uint64_t*)(dp + o_len), (int32_t*)(dp + o_gap), nblk, ctx->sm_count, st), "zpq_gaps_kernel launch");
+    CK(cudaMemcpyAsync(gaps, dp + o_gap, (size_t)nblk * 8, cudaMemcpyDeviceToHost, st), "D2H gaps");
+    ++ctx->launches;
+  }
+  CK(cudaEventRecord(ctx->ev[1], st), "event");
+  CK(cudaStreamSynchronize(st), "analysis");
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->ms_prep = ms;
+  return ZPQ_OK;
+}
+
+// Batched libzpaq::compressBlock (libzpaq.cpp:7543-7731), context-model family only.  `dev`: data[] and out[] are device
+// pointers (blocks scattered into HBM over NCCL); otherwise host pointers, staged through device buffers here.  Either
+// way everything per-byte runs on the device: SHA-1 and the level-5 gap statistics (zpq_prep.cu), the coding kernels, the
+// framing bytes around the coded data (a scatter kernel).  The host only turns (method, length, gaps) into header bytes.
+static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8_t* const* data,
+                         const uint64_t* len, const char* const* filenames, const char* const* comments,
+                         int dosha1, uint8_t* const* out, const uint64_t* out_cap, uint64_t* out_len,
+                         int32_t* status, bool dev) {
+  if (!ctx || nblk < 0 || !method || (nblk && (!data || !len || !out || !out_cap || !out_len))) return ZPQ_E_ARG;
+  if (nblk == 0) return ZPQ_OK;
+  CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t stream = ctx->stream;
+  const auto t_begin = std::chrono::steady_clock::now();
+  static const uint8_t kPass = 0;   // post-processor flag PASS goes through the model first (libzpaq.cpp:2914)
+  std::vector<int> st(nblk, ZPQ_OK);
+  for (int i = 0; i < nblk; ++i) if (len[i] > 0x7fffffffull - 4096) st[i] = ZPQ_E_ARG;
+
+  // ---- payloads in HBM ----
+  std::vector<const uint8_t*> d_data(nblk, nullptr);
+  if (dev) for (int i = 0; i < nblk; ++i) d_data[i] = data[i];
+  else {
+    uint64_t tot = 0;
+    std::vector<uint64_t> off(nblk);
+    for (int i = 0; i < nblk; ++i) { off[i] = tot; if (st[i] == ZPQ_OK) tot = align_up(tot + len[i] + 4, 16); }
+    CK(ctx->d_stage_in.reserve(tot + 16), "input staging cudaMalloc");
+    for (int i = 0; i < nblk; ++i) {
+      if (st[i] != ZPQ_OK) continue;
+      d_data[i] = (const uint8_t*)ctx->d_stage_in.p + off[i];
+      if (len[i]) CK(cudaMemcpyAsync((void*)d_data[i], data[i], len[i], cudaMemcpyHostToDevice, stream), "H2D input");
+    }
+  }
+  // ---- per-block analysis on the device: SHA-1, gap statistics of level 5 ----
+  const bool need_gaps = method_needs_gaps(method);
+  std::vector<uint8_t> sha((size_t)nblk * 20, 0);
+  std::vector<int32_t> gaps((size_t)nblk * 2, 0);
+  {
+    std::vector<uint64_t> alen(nblk);
+    for (int i = 0; i < nblk; ++i) alen[i] = st[i] == ZPQ_OK ? len[i] : 0;
+    std::vector<const uint8_t*> aptr(d_data);
+    for (int i = 0; i < nblk; ++i) if (!aptr[i]) aptr[i] = (const uint8_t*)ctx->d_tables;      // any valid address for an empty message
+    const int rc = analyze_dev(ctx, nblk, aptr.data(), alen.data(), dosha1 ? sha.data() : nullptr, need_gaps ? gaps.data() : nullptr);
+    if (rc != ZPQ_OK) return rc;
+  }
+  // ---- host: header bytes and block prologue from (method, length, gaps) ----
+  std::vector<std::vector<uint8_t>> hdrs(nblk), pro(nblk);
+  for (int i = 0; i < nblk; ++i) {
+    if (st[i] != ZPQ_OK) continue;
+    std::string e;
+    const int g2[2] = {gaps[2 * i], gaps[2 * i + 1]};
+    st[i] = header_from_stats(method, len[i], g2, &hdrs[i], &e);
+    if (st[i] != ZPQ_OK) continue;
+    char cs[32];
+    snprintf(cs, sizeof(cs), "%llu", (unsigned long long)len[i]);
+    std::string comment = cs;                                   // libzpaq.cpp:7702-7703
+    if (comments && comments[i]) { comment += " "; comment += comments[i]; }
+    write_block_prologue(&pro[i], hdrs[i].data(), (int)hdrs[i].size(), filenames ? filenames[i] : nullptr, comment.c_str());
+    const uint64_t tail = 4 + (dosha1 ? 21 : 1) + 1;
+    if (out_cap[i] < pro[i].size() + tail + 8) st[i] = ZPQ_E_OUTPUT_FULL;
+  }
+  // ---- output blocks in HBM ----
+  std::vector<uint8_t*> d_out(nblk, nullptr);
+  if (dev) for (int i = 0; i < nblk; ++i) d_out[i] = out[i];
+  else {
+    uint64_t tot = 0;
+    std::vector<uint64_t> off(nblk);
+    for (int i = 0; i < nblk; ++i) { off[i] = tot; if (st[i] == ZPQ_OK) tot = align_up(tot + out_cap[i], 16); }
+    CK(ctx->d_stage_out.reserve(tot + 16), "output staging cudaMalloc");
+    for (int i = 0; i < nblk; ++i) if (st[i] == ZPQ_OK) d_out[i] = (uint8_t*)ctx->d_stage_out.p + off[i];
+  }
+  // ---- the coding path ----
   std::vector<IJob> jobs;
   std::vector<int> idx;
   for (int i = 0; i < nblk; ++i) {
     if (st[i] != ZPQ_OK) continue;
     const uint64_t tail = 4 + (dosha1 ? 21 : 1) + 1;
-    if (out_cap[i] < pro[i].size() + tail + 8) { st[i] = ZPQ_E_OUTPUT_FULL; continue; }
     IJob J;
     J.hdr = hdrs[i].data(); J.hlen = (int)hdrs[i].size();
     J.in.push_back(Piece{&kPass, 1});
-    J.in.push_back(Piece{data[i], len[i]});
+    J.in.push_back(Piece{d_data[i], len[i]});
     J.seg_len.assign(1, len[i] + 1);
-    J.out = out[i] + pro[i].size();
+    J.out = d_out[i] + pro[i].size();
     J.out_cap = out_cap[i] - pro[i].size() - tail;
     jobs.push_back(J); idx.push_back(i);
   }
   int rc = run_batch(ctx, jobs, false, false);
-  for (size_t k = 0; k < jobs.size(); ++k) {
-    const int i = idx[k];
-    st[i] = jobs[k].status;
-    if (st[i] != ZPQ_OK) continue;
-    memcpy(out[i], pro[i].data(), pro[i].size());
-    uint8_t* p = out[i] + pro[i].size() + jobs[k].out_len;
-    p[0] = p[1] = p[2] = p[3] = 0;                       // Compressor::endSegment, libzpaq.cpp:2956-2966
-    p += 4;
-    if (dosha1) { *p++ = 253; memcpy(p, sha[i].data(), 20); p += 20; }
-    else *p++ = 254;
-    *p++ = 255;                                          // Compressor::endBlock, libzpaq.cpp:3002
-    out_len[i] = (uint64_t)(p - out[i]);
+  const float ms_init = ctx->ms[0] + ctx->ms_prep, ms_code = ctx->ms[1];
+  // ---- framing around the coded data (Compressor::endSegment / endBlock, libzpaq.cpp:2956-3002), written on the device ----
+  {
+    std::vector<uint8_t> pool; std::vector<uint64_t> src_off; std::vector<uint8_t*> dst; std::vector<uint32_t> nb;
+    for (size_t k = 0; k < jobs.size(); ++k) {
+      const int i = idx[k];
+      st[i] = jobs[k].status;
+      if (st[i] != ZPQ_OK) continue;
+      src_off.push_back(pool.size()); dst.push_back(d_out[i]); nb.push_back((uint32_t)pro[i].size());
+      pool.insert(pool.end(), pro[i].begin(), pro[i].end());
+      src_off.push_back(pool.size()); dst.push_back(d_out[i] + pro[i].size() + jobs[k].out_len);
+      const size_t t0 = pool.size();
+      pool.insert(pool.end(), 4, 0);
+      if (dosha1) { pool.push_back(253); pool.insert(pool.end(), sha.begin() + (size_t)i * 20, sha.begin() + (size_t)i * 20 + 20); }
+      else pool.push_back(254);
+      pool.push_back(255);
+      nb.push_back((uint32_t)(pool.size() - t0));
+      out_len[i] = pro[i].size() + jobs[k].out_len + (pool.size() - t0);
+    }
+    const int nrec = (int)dst.size();
+    if (nrec) {
+      const uint64_t o_pool = 0, o_src = align_up(pool.size(), 256), o_dst = o_src + align_up((uint64_t)nrec * 8, 256),
+                     o_nb = o_dst + align_up((uint64_t)nrec * 8, 256), total = o_nb + align_up((uint64_t)nrec * 4, 256);
+      CK(ctx->d_prep.reserve(total), "framing cudaMalloc");
+      uint8_t* dp = (uint8_t*)ctx->d_prep.p;
+      CK(cudaMemcpyAsync(dp + o_pool, pool.data(), pool.size(), cudaMemcpyHostToDevice, stream), "H2D framing");
+      CK(cudaMemcpyAsync(dp + o_src, src_off.data(), (size_t)nrec * 8, cudaMemcpyHostToDevice, stream), "H2D framing");
+      CK(cudaMemcpyAsync(dp + o_dst, dst.data(), (size_t)nrec * 8, cudaMemcpyHostToDevice, stream), "H2D framing");
+      CK(cudaMemcpyAsync(dp + o_nb, nb.data(), (size_t)nrec * 4, cudaMemcpyHostToDevice, stream), "H2D framing");
+      CK(zpq_launch_scatter(dp + o_pool, (const uint64_t*)(dp + o_src), (uint8_t* const*)(dp + o_dst), (const uint32_t*)(dp + o_nb), nrec, stream), "zpq_scatter_kernel launch");
+      ++ctx->launches;
+    }
+    if (!dev)
+      for (int i = 0; i < nblk; ++i)
+        if (st[i] == ZPQ_OK) CK(cudaMemcpyAsync(out[i], d_out[i], out_len[i], cudaMemcpyDeviceToHost, stream), "D2H blocks");
+    CK(cudaStreamSynchronize(stream), "framing");
   }
+  ctx->ms[0] = ms_init; ctx->ms[1] = ms_code;
+  ctx->ms[2] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   int first_bad = ZPQ_OK;
   for (int i = 0; i < nblk; ++i) {
     if (status) status[i] = st[i];
     if (st[i] != ZPQ_OK && first_bad == ZPQ_OK) first_bad = st[i];
   }
   return rc != ZPQ_OK ? rc : first_bad;
+}
+
+int zpq_compress_blocks(zpq_ctx* ctx, int nblk, const char* method, const uint8_t* const* data,
+                        const uint64_t* len, const char* const* filenames, const char* const* comments,
+                        int dosha1, uint8_t* const* out, const uint64_t* out_cap, uint64_t* out_len,
+                        int32_t* status) {
+  return compress_core(ctx, nblk, method, data, len, filenames, comments, dosha1, out, out_cap, out_len, status, false);
+}
+
+int zpq_compress_blocks_dev(zpq_ctx* ctx, int nblk, const char* method, const uint8_t* const* d_data,
+                            const uint64_t* len, const char* const* filenames, const char* const* comments,
+                            int dosha1, uint8_t* const* d_out, const uint64_t* out_cap, uint64_t* out_len,
+                            int32_t* status) {
+  return compress_core(ctx, nblk, method, d_data, len, filenames, comments, dosha1, d_out, out_cap, out_len, status, true);
+}
+
+int zpq_analyze_dev(zpq_ctx* ctx, int nblk, const uint8_t* const* d_data, const uint64_t* len, uint8_t* sha1, int32_t* gaps) {
+  if (!ctx || nblk < 0 || (nblk && (!d_data || !len))) return ZPQ_E_ARG;
+  return analyze_dev(ctx, nblk, d_data, len, sha1, gaps);
+}
+
+// Framing scan for callers that bind at the hot-path level (block sharding): one record per segment.
+int zpq_scan_archive(const uint8_t* arc, uint64_t arc_len, zpq_segment* segs, int cap, int* nsegs, int* nblocks) {
+  if (!arc || !nsegs) return ZPQ_E_ARG;
+  std::vector<BlockView> bv; std::string e;
+  const int rc = scan_archive(arc, arc_len, &bv, &e);
+  if (rc != ZPQ_OK) return rc;
+  int n = 0;
+  for (size_t b = 0; b < bv.size(); ++b)
+    for (size_t k = 0; k < bv[b].segs.size(); ++k, ++n) {
+      if (!segs || n >= cap) continue;
+      zpq_segment& S = segs[n];
+      const SegmentView& V = bv[b].segs[k];
+      S.block = (uint32_t)b; S.segment = (uint32_t)k;
+      S.hdr_off = bv[b].hdr_off; S.hlen = (uint32_t)bv[b].hlen; S.components = arc[bv[b].hdr_off + 6];
+      S.coded_off = V.coded_off; S.coded_len = V.coded_len;
+      S.has_sha1 = V.has_sha1 ? 1 : 0; memcpy(S.sha1, V.sha1, 20);
+      S.size_hint = comment_size_hint(arc, V);
+    }
+  *nsegs = n;
+  if (nblocks) *nblocks = (int)bv.size();
+  return (segs && n > cap) ? ZPQ_E_OUTPUT_FULL : ZPQ_OK;
 }
 
 // Batched libzpaq::decompress (libzpaq.cpp:2376-2389) over an in-memory archive.

@@ -27,6 +27,10 @@ int postprocess_block(int ph, int pm, const uint8_t* model_out, const uint64_t* 
 // zpq_method.cpp : method string (+ payload statistics) -> block header bytes
 int header_from_method(const char* method, const uint8_t* data, uint64_t n,
                        std::vector<uint8_t>* hdr, std::string* err);
+// the same with the payload statistics already taken (on the device: zpq_prep.cu): gaps[2] = dominant gaps, 0 = none
+bool method_needs_gaps(const char* method);
+void payload_gaps(const uint8_t* data, uint64_t n, int gaps[2]);
+int header_from_stats(const char* method, uint64_t n, const int gaps[2], std::vector<uint8_t>* hdr, std::string* err);
 
 // zpq_frame.cpp : SHA-1 and block framing
 struct Sha1 {

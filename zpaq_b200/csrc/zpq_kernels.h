@@ -22,6 +22,9 @@ int zpq_dec7_static_smem(void);
 int zpq_dec7_ctrl_bytes(void);
 int zpq_dec7_takes(unsigned long long sig);
 cudaError_t zpq_launch_dec7(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, unsigned long long sig, cudaStream_t st);
+cudaError_t zpq_launch_sha1(const uint8_t* const* ptr, const uint64_t* len, uint8_t* out, int n, cudaStream_t st);
+cudaError_t zpq_launch_gaps(const uint8_t* const* ptr, const uint64_t* len, int32_t* gaps, int n, int sm_count, cudaStream_t st);
+cudaError_t zpq_launch_scatter(const uint8_t* pool, const uint64_t* src_off, uint8_t* const* dst, const uint32_t* nbytes, int n, cudaStream_t st);
 cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant);
 unsigned long long zpq_code2_signature(const ZFast* F);
 cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int decode, int sm_count, int warps, int pw_bytes,

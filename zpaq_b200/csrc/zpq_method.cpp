@@ -87,7 +87,7 @@ std::vector<int> dominant_gaps(const uint8_t* p, unsigned n) {
 
 // "LB[,R,T]": L = level digit, B = block size digits (ignored here: the block decides), R,T -> block type R*4+T
 // (bit 0 text, bit 1 exe; 512 when no type is given).  Only the context-mixing branches of levels 4 and 5 are in scope.
-int level_tokens(const std::string& m, const uint8_t* p, uint64_t n64, int* arg0, std::vector<Token>* out, std::string* err) {
+int level_tokens(const std::string& m, uint64_t n64, const std::vector<int>& gaps, int* arg0, std::vector<Token>* out, std::string* err) {
   const unsigned n = (unsigned)n64;
   *arg0 = std::max(bit_length(n + 4095) - 20, 0);
   int field[4] = {0, 0, 0, 0}, nsep = 0;
@@ -122,7 +122,7 @@ int level_tokens(const std::string& m, const uint8_t* p, uint64_t n64, int* arg0
   t.push_back(tok('c'));
   t.push_back(tok('i', {1, 1, 1, 1, 1, 1, 2}));
   t.push_back(tok('a'));
-  for (int gap : dominant_gaps(p, n)) {
+  for (int gap : gaps) {
     t.push_back(tok('c', {0, 0, 999 + gap, 255})); t.push_back(tok('i', {1}));            // the byte one period back
     if (gap <= 255) { t.push_back(tok('c', {0, gap})); t.push_back(tok('i', {1})); }      // position inside the period
   }
@@ -353,7 +353,24 @@ int serialise(const Draft& d, std::vector<uint8_t>* hdr, std::string* err) {
 
 }  // namespace
 
+// a digit method of level 5 and up looks at the payload (gap statistics); everything else is decided by the text alone
+bool method_needs_gaps(const char* method) {
+  return method && isdigit((unsigned char)method[0]) && method[0] >= '5';
+}
+
+void payload_gaps(const uint8_t* data, uint64_t n, int gaps[2]) {
+  gaps[0] = gaps[1] = 0;
+  const std::vector<int> g = dominant_gaps(data, (unsigned)n);
+  for (size_t i = 0; i < g.size() && i < 2; ++i) gaps[i] = g[i];
+}
+
 int header_from_method(const char* method_, const uint8_t* data, uint64_t n, std::vector<uint8_t>* hdr, std::string* err) {
+  int gaps[2] = {0, 0};
+  if (method_needs_gaps(method_) && n <= 0x7fffffffull - 4096) payload_gaps(data, n, gaps);
+  return header_from_stats(method_, n, gaps, hdr, err);
+}
+
+int header_from_stats(const char* method_, uint64_t n, const int gaps_in[2], std::vector<uint8_t>* hdr, std::string* err) {
   std::string e0;
   if (!err) err = &e0;
   if (!method_ || !method_[0]) { *err = "empty method"; return ZPQ_E_METHOD; }
@@ -362,7 +379,9 @@ int header_from_method(const char* method_, const uint8_t* data, uint64_t n, std
   std::vector<Token> tokens;
   int size_class = 0, preprocessing = 0;
   if (isdigit((unsigned char)ms[0])) {
-    const int rc = level_tokens(ms, data, n, &size_class, &tokens, err);
+    std::vector<int> gaps;
+    for (int i = 0; i < 2 && gaps_in && gaps_in[i] > 0; ++i) gaps.push_back(gaps_in[i]);
+    const int rc = level_tokens(ms, n, gaps, &size_class, &tokens, err);
     if (rc != ZPQ_OK) return rc;
   }
   else if (ms[0] == 'x') {
