@@ -67,7 +67,7 @@ struct zpq_ctx {
   uint64_t launches = 0;
   uint32_t tiers[6] = {0, 0, 0, 0, 0, 0};   // blocks of the last batch per kernel tier (zpq_last_tiers)
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
-  int wave_chunk = 2048;       // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two)
+  int wave_chunk = 512;        // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two; 512 measured best in round 2: profiles/r02c)
   int wave_variant = 25;       // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps, bit 4 nibble-unrolled ICM / ISSE loop
   int dec_variant = 31;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7 or 15) slot-scheduled hashes, bit 3 (15) MATCH in warp A, bit 4 (31) register-resident predictions in warp B
   int wave_role_major = 1;     // ZPQ_WAVE_ORDER: 1 = role-major warp order of the wavefront encoder (default), 0 = group-major (round 1)
@@ -182,6 +182,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     const int kv = ctx->kernel_version;
     auto kclass = [&](int i) -> int {
       const ZModel& Mi = models[jobs[i].model];
+      if (Mi.wide) return 5;                                 // more than 32 components: one thread per block (zpq_kernels.cu)
       if (kv == 1) return 4;
       if (!decode && kv >= 5 && Mi.wave.ok) return 0;
       return Mi.fast.ok ? 3 : 4;
@@ -191,7 +192,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
       const int ca = kclass(a), cb = kclass(b);
       return ca != cb ? ca < cb : jobs[a].model < jobs[b].model;
     });
-    int ncls[5] = {0, 0, 0, 0, 0};
+    int ncls[6] = {0, 0, 0, 0, 0, 0};
     for (int i : wave) ++ncls[kclass(i)];
 
     std::vector<ZBlock> blocks(nb);
@@ -275,13 +276,14 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
     CK(cudaEventRecord(ev[2], st), "event");
     {
       int first = 0;
-      for (int cls = 0; cls < 5; ++cls) {
+      for (int cls = 0; cls < 6; ++cls) {
         const int cnt = ncls[cls];
         if (cnt == 0) continue;
         ZKernelArgs Ak = A;
         Ak.blocks = A.blocks + first; Ak.status = A.status + first; Ak.out_len = A.out_len + first;
         Ak.counter = A.counter + cls; Ak.nblk = cnt;
-        if (cls == 4) { CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch"); ++ctx->launches; ctx->tiers[4] += (uint32_t)cnt; }
+        if (cls == 5) { CK(zpq_launch_wide(&Ak, cnt, decode ? 1 : 0, st), "zpq_wide_kernel launch"); ++ctx->launches; ctx->tiers[5] += (uint32_t)cnt; }
+        else if (cls == 4) { CK(zpq_launch_code(&Ak, cnt, decode ? 1 : 0, ctx->sm_count, st), "zpq_code_kernel launch"); ++ctx->launches; ctx->tiers[4] += (uint32_t)cnt; }
         else if (cls == 0) {
           // ---- wavefront encoder: groups of <= 32 blocks of one model, one launch per wave ----
           const int GS = ctx->wave_group;

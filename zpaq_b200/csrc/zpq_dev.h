@@ -157,6 +157,11 @@ struct ZHashPlan {
   alignas(8) ZHashSlot slot[ZPQ_HSLOTS];
   uint32_t w[ZPQ_HSLOTS][32];            // operand word per lane (the flat op word; ZH_SEG: segment index in bits 8-9)
   uint32_t w2[ZPQ_HSLOTS][32];           // ZH_WORD: second word (multiplier, first flag)
+  // the two-warp decoders split the components over two warps (role 0: ICM ISSE CM CONST MATCH, role 1: the rest): the
+  // slots that touch a lane of each role, so that a warp walks only its own slots (zpq_kernels7.cu)
+  uint8_t role_n[2];
+  uint8_t role_slots[2][ZPQ_HSLOTS];
+  uint32_t role_fold[2];                 // fold lanes of each role
 };
 
 // Team plan (round-1 three-warp encoder, removed; the wavefront encoder still reads nmix / mix_comp): the skewed pipeline of ZPipe split over THREE warps per block so that
@@ -189,6 +194,12 @@ struct ZModel {
   uint32_t m_off16, h_off16, r_off16;
   uint32_t m_mask, h_mask;
   uint64_t arena_bytes;   // multiple of 256
+  // models with more than 32 components (up to the format's 255): coded by the wide kernel, one thread per block; their
+  // component and fill lists do not fit the fixed arrays below and follow the program image in the program pool
+  uint32_t wide;          // 1: wide model
+  uint32_t wide_comp_off; // byte offset from prog_off of ZComp[n]
+  uint32_t wide_fill_off; // byte offset from prog_off of ZFill[nfills]
+  uint32_t wst_off16;     // arena: per-component dynamic state, 8 words each (zero filled)
   ZComp comp[ZPQ_MAX_LANES];
   ZStep steps[ZPQ_MAX_STEPS];
   ZFill fills[ZPQ_MAX_FILLS];

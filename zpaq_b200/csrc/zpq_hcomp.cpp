@@ -549,6 +549,19 @@ void build_hash_plan(ZModel* M) {
     ++ns;
   }
   P.nslots = ns;
+  // per-role slot lists (two-warp decoders)
+  {
+    uint32_t role_mask[2] = {0, 0};
+    for (int l = 0; l < n; ++l) {
+      const uint32_t t = M->comp[l].type;
+      const int role = (t == ZT_ICM || t == ZT_ISSE || t == ZT_CM || t == ZT_CONS || t == ZT_MATCH) ? 0 : 1;
+      role_mask[role] |= 1u << l;
+    }
+    for (int r = 0; r < 2; ++r) {
+      P.role_n[r] = 0; P.role_fold[r] = P.fold_lanes & role_mask[r];
+      for (uint32_t s2 = 0; s2 < ns; ++s2) if (P.slot[s2].lanes & role_mask[r]) P.role_slots[r][P.role_n[r]++] = (uint8_t)s2;
+    }
+  }
   // self-check against the flat form (which build_wave_plan checked against the recipes, which build_recipes
   // checked against the bytecode)
   std::vector<FlatEval> fe(n);

@@ -52,8 +52,9 @@ __global__ void __launch_bounds__(256) zpq_init_kernel(const ZKernelArgs A) {
   const ZTables* __restrict__ T = A.tables;
   const u32 nf = M->nfills;
   const u32 stride = gridDim.x * blockDim.x;
+  const ZFill* __restrict__ fills = M->wide ? reinterpret_cast<const ZFill*>(A.progs + M->prog_off + M->wide_fill_off) : M->fills;
   for (u32 f = 0; f < nf; ++f) {
-    const ZFill F = M->fills[f];
+    const ZFill F = fills[f];
     uint4* dst = reinterpret_cast<uint4*>(arena + (u64)F.off16 * 16);
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < F.n16; i += stride) {
       uint4 v = make_uint4(0, 0, 0, 0);
@@ -625,6 +626,261 @@ __global__ void __launch_bounds__(ZPQ_WARPS * 32, 2) zpq_code_kernel(const ZKern
     if (!DEC && status == ST_OK && C.status != ST_OK) status = C.status;
     if (lane == 0) { A.status[blk] = status; A.out_len[blk] = C.out_pos; }
   }
+}
+
+// ---------------------------------------------------------------------------
+// WIDE models: 33 .. 255 components (Predictor holds comp[256], libzpaq.h:1131-1137).  The lane = component mapping of
+// the kernels above stops at 32, so these blocks are coded by ONE THREAD each, walking the components in order exactly as
+// Predictor::predict0 / update0 do (libzpaq.cpp:1854-2066); every table, the hash rows and the per-component registers
+// (Component::cxt, a, b, c, limit) live in the block's arena, the static tables are read through the read-only path.  It is
+// a completeness tier (makeConfig stops at ~30 components; hand-written configs can go further), not a fast one: lanes
+// of a warp are different blocks, possibly of different models.
+struct WideState { u32 cxt, a, b, c, limit, row, pad0, pad1; };    // 8 words per component in the arena (ZModel.wst_off16)
+
+__device__ __forceinline__ int w_stretch(const ZTables* T, u32 x) {
+  return x >= 16384u ? (int)__ldg(&T->stretch_hi[x - 16384u]) : -(int)__ldg(&T->stretch_hi[16383u - x]);
+}
+__device__ __forceinline__ int w_squash(const ZTables* T, int x) { return (int)__ldg(&T->squash[x + 2048]); }
+
+// Predictor::find on the table itself (libzpaq.cpp:2072-2088): returns the row's byte offset
+__device__ __forceinline__ u32 w_find(u8* ht, u32 ht_mask, int shift, u32 cxt) {
+  const u32 chk = (cxt >> shift) & 255u;
+  const u32 h0 = (cxt * 16u) & ht_mask, h1 = h0 ^ 16u, h2 = h0 ^ 32u;
+  if (ht[h0] == chk) return h0;
+  if (ht[h1] == chk) return h1;
+  if (ht[h2] == chk) return h2;
+  u32 r;
+  if (ht[h0 + 1] <= ht[h1 + 1] && ht[h0 + 1] <= ht[h2 + 1]) r = h0;
+  else if (ht[h1 + 1] < ht[h2 + 1]) r = h1;
+  else r = h2;
+  *reinterpret_cast<uint4*>(ht + r) = make_uint4(chk, 0, 0, 0);
+  return r;
+}
+
+template <bool DEC>
+__global__ void __launch_bounds__(32) zpq_wide_kernel(const ZKernelArgs A) {
+  const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= A.nblk) return;
+  const ZBlock B = A.blocks[blk];
+  const ZModel* __restrict__ ZM = A.models + B.model;
+  const ZTables* __restrict__ T = A.tables;
+  u8* const arena = A.arena + B.arena_off;
+  const int n = (int)ZM->n;
+  const ZComp* __restrict__ comp = reinterpret_cast<const ZComp*>(A.progs + ZM->prog_off + ZM->wide_comp_off);
+  WideState* const ws = reinterpret_cast<WideState*>(arena + (u64)ZM->wst_off16 * 16);
+  int p[256];
+  for (int i = 0; i < n; ++i) p[i] = comp[i].type == ZT_CONS ? ((int)comp[i].a1 - 128) * 4 : 0;      // libzpaq.cpp:1775
+
+  VmState V;
+  V.a = V.b = V.c = V.d = V.f = 0;
+  V.m = arena + (u64)ZM->m_off16 * 16;
+  V.h = reinterpret_cast<u32*>(arena + (u64)ZM->h_off16 * 16);
+  V.r = reinterpret_cast<u32*>(arena + (u64)ZM->r_off16 * 16);
+  V.mmask = ZM->m_mask; V.hmask = ZM->h_mask;
+  V.len = (int)ZM->prog_len;
+  V.code = A.progs + ZM->prog_off + ZPQ_GUARD_LO;
+
+  Coder C;
+  C.low = 1; C.high = 0xffffffffu; C.curr = 0; C.status = ST_OK;
+  C.in = A.in + B.in_off; C.in_pos = 0; C.in_end = 0;
+  C.out = A.out + B.out_off; C.out_pos = 0; C.out_cap = B.out_cap;
+  int c8 = 1, hmap4 = 1;
+  int status = ST_OK;
+
+  for (u32 sg = 0; sg < B.nseg && status == ST_OK; ++sg) {
+    const u64 seg_n = A.seg_len[B.seg_first + sg];
+    const u64 out_start = C.out_pos;
+    C.in_end = C.in_pos + seg_n;
+    if constexpr (DEC) {
+      C.curr = 0;
+      for (int i = 0; i < 4; ++i) {
+        if (C.in_pos >= C.in_end) { status = ST_EOF; break; }
+        C.curr = C.curr << 8 | (u32)C.in[C.in_pos++];
+      }
+    }
+    for (;;) {
+      if (status != ST_OK) break;
+      int cbyte = 0;
+      if constexpr (!DEC) {
+        if (C.in_pos >= C.in_end) break;
+        cbyte = C.in[C.in_pos++];
+        enc_bit(C, 0, 0, 0);
+      } else {
+        const int eos = dec_bit(C, 0);
+        if (C.status != ST_OK) { status = C.status; break; }
+        if (eos) { if (C.curr != 0) status = ST_EOS; break; }
+      }
+      for (int bit = 7; bit >= 0; --bit) {
+        // ---------------- predict0 ----------------
+        const bool nib = (c8 == 1) || ((c8 & 0xf0) == 16);
+        for (int i = 0; i < n; ++i) {
+          const ZComp cd = comp[i];
+          WideState& W = ws[i];
+          u32* cm = reinterpret_cast<u32*>(arena + (u64)cd.cm_off16 * 16);
+          u8* ht = arena + (u64)cd.ht_off16 * 16;
+          const u32 h = V.h[(u32)i & V.hmask];               // H(i) wraps modulo 2^hh (libzpaq.h:1040)
+          switch (cd.type) {
+            case ZT_CM:
+              W.cxt = (h ^ (u32)hmap4) & cd.cm_mask;
+              p[i] = w_stretch(T, cm[W.cxt] >> 17);
+              break;
+            case ZT_ICM:
+              if (nib) W.row = w_find(ht, cd.ht_mask, (int)cd.a1 + 2, h + 16u * (u32)c8);
+              W.cxt = ht[W.row + (u32)(hmap4 & 15)];
+              p[i] = w_stretch(T, cm[W.cxt] >> 8);
+              break;
+            case ZT_MATCH:
+              if (W.a == 0) p[i] = 0;
+              else {
+                W.c = ((u32)ht[(W.limit - W.b) & cd.ht_mask] >> (7 - W.cxt)) & 1u;
+                p[i] = w_stretch(T, (u32)((int)__ldg(&T->dt2k[W.a]) * (1 - 2 * (int)W.c)) & 32767u);
+              }
+              break;
+            case ZT_AVG:
+              p[i] = (p[cd.a1] * (int)cd.a3 + p[cd.a2] * (256 - (int)cd.a3)) >> 8;
+              break;
+            case ZT_MIX2: {
+              W.cxt = (h + (u32)(c8 & (int)cd.a5)) & cd.cm_mask;
+              const int w = (int)reinterpret_cast<const u16*>(cm)[W.cxt];
+              p[i] = (w * p[cd.a2] + (65536 - w) * p[cd.a3]) >> 16;
+              break;
+            }
+            case ZT_MIX: {
+              const int m = (int)cd.a3;
+              W.cxt = ((h + (u32)(c8 & (int)cd.a5)) & cd.cm_mask) * (u32)m;
+              const int* wt = reinterpret_cast<const int*>(cm) + W.cxt;
+              int sum = 0;
+              for (int j = 0; j < m; ++j) sum += (wt[j] >> 8) * p[(int)cd.a2 + j];
+              p[i] = clamp2k(sum >> 8);
+              break;
+            }
+            case ZT_ISSE: {
+              if (nib) W.row = w_find(ht, cd.ht_mask, (int)cd.a1 + 2, h + 16u * (u32)c8);
+              W.cxt = ht[W.row + (u32)(hmap4 & 15)];
+              const int* wt = reinterpret_cast<const int*>(cm) + W.cxt * 2;
+              p[i] = clamp2k((wt[0] * p[cd.a2] + wt[1] * 64) >> 16);
+              break;
+            }
+            case ZT_SSE: {
+              W.cxt = (h + (u32)c8) * 32u;
+              int pq = min(max(p[cd.a2] + 992, 0), 1983);
+              const int wt = pq & 63;
+              pq >>= 6;
+              W.cxt += (u32)pq;
+              p[i] = w_stretch(T, (u32)(((int)(cm[W.cxt & cd.cm_mask] >> 10) * (64 - wt) + (int)(cm[(W.cxt + 1u) & cd.cm_mask] >> 10) * wt) >> 13));
+              W.cxt += (u32)(wt >> 5);
+              break;
+            }
+            default: break;   // CONS
+          }
+        }
+        const u32 p16 = (u32)w_squash(T, p[n - 1]) * 2u + 1u;
+        int y;
+        if constexpr (!DEC) { y = (cbyte >> bit) & 1; enc_bit(C, 0, y, p16); }
+        else {
+          y = dec_bit(C, p16);
+          if (C.status != ST_OK) { status = C.status; break; }
+        }
+        // ---------------- update0 ----------------
+        for (int i = 0; i < n; ++i) {
+          const ZComp cd = comp[i];
+          WideState& W = ws[i];
+          u32* cm = reinterpret_cast<u32*>(arena + (u64)cd.cm_off16 * 16);
+          u8* ht = arena + (u64)cd.ht_off16 * 16;
+          switch (cd.type) {
+            case ZT_CM: case ZT_SSE: {     // train(), libzpaq.h:1151-1157
+              u32& pn = cm[W.cxt & cd.cm_mask];
+              const u32 count = pn & 0x3ffu;
+              const int err = y * 32767 - (int)(pn >> 17);
+              pn += (((u32)err * (u32)__ldg(&T->dt[count])) & 0xfffffc00u) + (count < cd.limit ? 1u : 0u);
+              break;
+            }
+            case ZT_ICM: {
+              ht[W.row + (u32)(hmap4 & 15)] = (u8)((__ldg(&T->ns[W.cxt]) >> (8 * y)) & 255u);
+              u32& pn = cm[W.cxt];
+              pn += (u32)(((int)(y * 32767 - (int)(pn >> 8))) >> 2);
+              break;
+            }
+            case ZT_MATCH: {
+              // libzpaq.cpp:1990-2008; h[i] is still the previous byte's hash here (gotcha 6)
+              if ((int)W.c != y) W.a = 0;
+              u8& cur = ht[W.limit & cd.ht_mask];
+              cur = (u8)(cur * 2 + y);
+              if (++W.cxt == 8) {
+                W.cxt = 0;
+                W.limit = (W.limit + 1) & cd.ht_mask;
+                u32& idx = cm[V.h[(u32)i & V.hmask] & cd.cm_mask];
+                if (W.a == 0) {
+                  W.b = W.limit - idx;
+                  if (W.b & cd.ht_mask)
+                    while (W.a < 255 && ht[(W.limit - W.a - 1) & cd.ht_mask] == ht[(W.limit - W.a - W.b - 1) & cd.ht_mask]) ++W.a;
+                }
+                else W.a += (W.a < 255);
+                idx = W.limit;
+              }
+              break;
+            }
+            case ZT_MIX2: {
+              const int err = ((y * 32767 - w_squash(T, p[i])) * (int)cd.a4) >> 5;
+              int w = (int)reinterpret_cast<u16*>(cm)[W.cxt];
+              w += (err * (p[cd.a2] - p[cd.a3]) + (1 << 12)) >> 13;
+              w = min(max(w, 0), 65535);
+              reinterpret_cast<u16*>(cm)[W.cxt] = (u16)w;
+              break;
+            }
+            case ZT_MIX: {
+              const int m = (int)cd.a3;
+              const int err = ((y * 32767 - w_squash(T, p[i])) * (int)cd.a4) >> 4;
+              int* wt = reinterpret_cast<int*>(cm) + W.cxt;
+              for (int j = 0; j < m; ++j) wt[j] = clamp512k(wt[j] + ((err * p[(int)cd.a2 + j] + (1 << 12)) >> 13));
+              break;
+            }
+            case ZT_ISSE: {
+              const int err = y * 32767 - w_squash(T, p[i]);
+              int* wt = reinterpret_cast<int*>(cm) + W.cxt * 2;
+              wt[0] = clamp512k(wt[0] + ((err * p[cd.a2] + (1 << 12)) >> 13));
+              wt[1] = clamp512k(wt[1] + ((err + 16) >> 5));
+              ht[W.row + (u32)(hmap4 & 15)] = (u8)((__ldg(&T->ns[W.cxt]) >> (8 * y)) & 255u);
+              break;
+            }
+            default: break;
+          }
+        }
+        const int c8n = c8 * 2 + y;
+        if (c8n >= 256) {
+          const int rc = vm_run(V, (u32)(c8n - 256));
+          if (rc != ST_OK) { status = rc; break; }
+          hmap4 = 1; c8 = 1;
+          if (DEC) cbyte = c8n - 256;
+        } else {
+          c8 = c8n;
+          if (c8n >= 16 && c8n < 32) hmap4 = (hmap4 & 0xf) << 5 | y << 4 | 1;
+          else hmap4 = (hmap4 & 0x1f0) | (((hmap4 & 0xf) * 2 + y) & 0xf);
+        }
+      }
+      if (DEC && status == ST_OK) {
+        if (C.out_pos < C.out_cap) C.out[C.out_pos] = (u8)cbyte;
+        else status = ST_FULL;
+        ++C.out_pos;
+      }
+    }
+    if (!DEC && status == ST_OK) {
+      enc_bit(C, 0, 1, 0);
+      if (C.status != ST_OK) status = C.status;
+    }
+    if (DEC && status == ST_OK && C.in_pos != C.in_end) status = ST_CORRUPT;
+    A.seg_out[B.seg_first + sg] = C.out_pos - out_start;
+  }
+  if (!DEC && status == ST_OK && C.status != ST_OK) status = C.status;
+  A.status[blk] = status; A.out_len[blk] = C.out_pos;
+}
+
+extern "C" cudaError_t zpq_launch_wide(const ZKernelArgs* a, int nblk, int decode, cudaStream_t st) {
+  if (nblk <= 0) return cudaSuccess;
+  const int ctas = (nblk + 31) / 32;
+  if (decode) zpq_wide_kernel<true><<<ctas, 32, 0, st>>>(*a);
+  else zpq_wide_kernel<false><<<ctas, 32, 0, st>>>(*a);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------

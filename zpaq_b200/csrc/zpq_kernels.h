@@ -12,6 +12,7 @@ extern "C" {
 size_t zpq_code_kernel_smem(void);
 cudaError_t zpq_launch_init(const ZKernelArgs* a, int nblk, cudaStream_t st);
 cudaError_t zpq_launch_code(const ZKernelArgs* a, int nblk, int decode, int sm_count, cudaStream_t st);
+cudaError_t zpq_launch_wide(const ZKernelArgs* a, int nblk, int decode, cudaStream_t st);
 // v2 (production) kernel: one CTA per SM, `warps` blocks in flight per CTA,
 // `pw_bytes` of shared memory per warp for the ICM/ISSE tables.
 int zpq_code2_static_smem(void);

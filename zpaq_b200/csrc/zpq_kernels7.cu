@@ -87,6 +87,78 @@ __device__ __forceinline__ void find7(const u8* ht, u32 ht_mask, int shift, u32 
   else { row = make_uint4(chk, 0, 0, 0); off = repl; }
 }
 
+// hplan_eval (zpq_kcommon.cuh) over the slots of ONE role only: `list` / `nl` = ZHashPlan.role_slots / role_n of the warp's
+// role.  Every listed slot has at least one lane of this warp, so there is nothing to skip.
+__device__ __forceinline__ u32 hplan_eval7(const ZHashPlan* __restrict__ P, const u8* __restrict__ list, int nl, u32 fold_mask, u32 mine_mask,
+                                           int lane, u32 last_seg, u32 fold_n1, u32 st[ZPQ_FLAT_SEGS], u32 cur, u64 hs, u32 vc,
+                                           const u8* ring, u32 ring_mask, u32 dist_last, u32 h_old) {
+  u32 accf = 0;
+  if (fold_mask) {                                         // warp-uniform
+#pragma unroll
+    for (u32 k = 0; k < 8; ++k) {
+      const u32 nx = (accf + ((u32)(hs >> (8u * k)) & 255u) + 512u) * 773u;
+      if (k + 1u < fold_n1) accf = nx;
+    }
+  }
+  u32 acc = 0, prev_new = 0, prev_old = 0;
+  const uint2* __restrict__ sd = reinterpret_cast<const uint2*>(P->slot);
+  int sn = nl > 0 ? (int)__ldg(list) : 0;
+  uint2 dn = __ldg(sd + sn);
+  u32 wn = __ldg(&P->w[sn][lane]);
+  for (int k = 0; k < nl; ++k) {
+    const int s = sn;
+    const u32 lm = dn.x, kind = dn.y, w = wn;
+    if (k + 1 < nl) { sn = (int)__ldg(list + k + 1); dn = __ldg(sd + sn); wn = __ldg(&P->w[sn][lane]); }
+    const bool on = (lm >> lane) & 1u;
+    const u32 src = (w >> 4) & 15u, arg = (w >> 8) & 255u, off = w >> 16;
+    if (kind == ZH_FOLD_BYTE) {
+      const u32 x = (u32)(hs >> ((off & 7u) * 8u)) & arg;
+      if (on) acc = (acc + x + 512u) * 773u;
+    }
+    else if (kind == ZH_SEG) {
+      const u32 kk = arg & 3u;
+      if (on) {
+        if (kk > 0u) {
+          const u32 old = kk == 1u ? st[0] : (kk == 2u ? st[1] : st[2]);
+          if (kk == 1u) st[0] = acc; else if (kk == 2u) st[1] = acc; else st[2] = acc;
+          prev_old = old; prev_new = acc;
+        }
+        const u32 own = kk == 0u ? st[0] : (kk == 1u ? st[1] : (kk == 2u ? st[2] : st[3]));
+        acc = src == ZB_ZERO ? 0u : (src == ZB_OWN ? own : prev_new);
+      }
+    }
+    else if (kind == ZH_SHL8_BYTE) {
+      const u32 x = (u32)(hs >> ((off & 7u) * 8u)) & arg;
+      if (on) acc = (acc << 8) + x;
+    }
+    else if (kind == ZH_FOLD_OTHER || kind == ZH_SHL8_OTHER) {
+      if (on) {
+        u32 x = 0;
+        if (src == ZS_BYTE) x = (u32)ring[(vc + off) & ring_mask] & arg;
+        else if (src == ZS_POSAND) x = vc & arg;
+        else if (src == ZS_POSMOD) x = arg ? vc % arg : 0u;
+        else if (src == ZS_DIST) x = min(dist_last - vc, 255u);
+        acc = kind == ZH_FOLD_OTHER ? (acc + x + 512u) * 773u : (acc << 8) + x;
+      }
+    }
+    else if (kind == ZH_SHR) { if (on) acc >>= arg; }
+    else if (kind == ZH_SHL) { if (on) acc <<= arg; }
+    else if (kind == ZH_ROLL) { if (on) acc = acc * off + cur + 1u; }
+    else if (kind == ZH_WORD) {
+      const u32 w2 = __ldg(&P->w2[s][lane]);
+      const u32 v2 = off & 255u, v3 = off >> 8, mult = w2 & 255u, first = (w2 >> 8) & 1u;
+      if (on) {
+        if ((((cur & arg) - v2) & 255u) < v3) acc = acc * mult + cur + 1u;
+        else acc = first ? 0u : prev_old;
+      }
+    }
+  }
+  if (!((mine_mask >> lane) & 1u)) return h_old;
+  if (fold_n1) { st[0] = accf; return accf; }
+  if (last_seg == 0u) st[0] = acc; else if (last_seg == 1u) st[1] = acc; else if (last_seg == 2u) st[2] = acc; else st[3] = acc;
+  return acc;
+}
+
 template <unsigned long long SIG>
 __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, const int pw_bytes, const int nteams) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -146,6 +218,9 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
     const u32 mine_mask = __ballot_sync(FULL, mine);
     const u32 hp_last = (lane < n) ? (u32)HP->last_seg[lane] : 0u;
     const u32 hp_fold = (lane < n) ? (u32)HP->fold_n[lane] : 0u;
+    const u8* __restrict__ hp_list = HP->role_slots[role];
+    const int hp_nl = (int)HP->role_n[role];
+    const u32 hp_foldm = HP->role_fold[role];
     const u32 tabw = wbase + ((lane < n) ? ZM->fast.smem_off[lane] : 0u) / 4u;
     const u32 dist_byte = mine ? ZM->pipe.dist_byte[lane] : 0u;
     u32 st[ZPQ_FLAT_SEGS] = {0, 0, 0, 0};
@@ -161,7 +236,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
       vm_c -= 1; mring[vm_c & mmask] = (u8)bv_;          /* both warps write the same value */       \
       hist = (hist << 8) | (u64)bv_;                                                                 \
       if (mine && bv_ == dist_byte) dist_last = vm_c;                                                \
-      h = hplan_eval(HP, mine_mask, lane, hp_last, hp_fold, st, bv_, hist, vm_c, mring, mmask, dist_last, h);   \
+      h = hplan_eval7(HP, hp_list, hp_nl, hp_foldm, mine_mask, lane, hp_last, hp_fold, st, bv_, hist, vm_c, mring, mmask, dist_last, h);   \
       hmap4 = 1; c8 = 1;                                                                             \
     } while (0)
 
@@ -178,7 +253,8 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
       const bool hashl = type == ZT_ICM || type == ZT_ISSE;
       const bool isse = type == ZT_ISSE;
       const u32 tw2 = isse ? 2u : 1u, tw1 = isse ? 1u : 0u;      // words per table entry; offset of the second word
-      const int nlev = (int)ZM->fast.nlev;
+      constexpr int NLEV = sig7_count(SIG, ZPQ_FAST_STEPS, ZK_ISSE);      // ISSE levels of the signature (= fast.nlev)
+      const int mylev = isse ? (int)level : 0;
       const int jsrc = (int)a2 & 31;
       uint4 row = make_uint4(0, 0, 0, 0); u32 row_off = 0;
       u32 hs = 1;                                                // slot inside the row = hmap4 & 15
@@ -207,11 +283,16 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
         for (;;) {
           // ---------------- predict (critical path): ISSE chain, publish ----------------
           int p = p_own, xj = 0;
-#pragma unroll 1
-          for (int lev = 1; lev <= nlev; ++lev) {
-            const int pj = __shfl_sync(FULL, p, jsrc);
-            const int q = clamp2k(((int)v0 * pj + (int)v1 * 64) >> 16);
-            if (isse && level == (u32)lev) { xj = pj; p = q; }
+          {
+            // the chain, one level per step of the signature: shuffle, multiply-add, shift, clamp, two selects
+            const int c64 = (int)v1 * 64;
+#pragma unroll
+            for (int lev = 1; lev <= NLEV; ++lev) {
+              const int pj = __shfl_sync(FULL, p, jsrc);
+              const int q = clamp2k(((int)v0 * pj + c64) >> 16);
+              const bool on = mylev == lev;
+              xj = on ? pj : xj; p = on ? q : p;
+            }
           }
           if (mine) pp[lane] = (short)p;
           BAR_ARRIVE64(barP);
@@ -360,21 +441,6 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
       // the last component is produced by the last step of this warp (else it is one of warp A's)
       const u32 sd_last = nsteps > 0 ? ZM->fast.sd[nsteps - 1] : 0u;
       const bool fin_in_b = nsteps > 0 && (sd_last & 7u) != ZK_ISSE && (int)((sd_last >> 3) & 31u) == n - 1;
-      // for every step: which EARLIER step (bit mask over step indexes) produces its inputs j / k; 0 = a component of warp A
-      u32 srcj[ZPQ_FAST_STEPS], srck[ZPQ_FAST_STEPS];
-#pragma unroll
-      for (int s = 0; s < ZPQ_FAST_STEPS; ++s) {
-        srcj[s] = 0; srck[s] = 0;
-        const u32 kd = sd[s] & 7u;
-        const u32 sj = (sd[s] >> 8) & 31u, sk = (sd[s] >> 13) & 63u;
-#pragma unroll
-        for (int e = 0; e < ZPQ_FAST_STEPS; ++e)
-          if (e < s && e < nsteps && (sd[e] & 7u) != ZK_ISSE) {
-            const u32 ow = (sd[e] >> 3) & 31u;
-            if (ow == sj) srcj[s] = 1u << e;
-            if (ow == (sk & 31u) && (kd == ZK_MIX2 || kd == ZK_AVG)) srck[s] = 1u << e;
-          }
-      }
       int* mix_tab[ZPQ_FAST_MIX]; u32 mix_owner[ZPQ_FAST_MIX], mix_m[ZPQ_FAST_MIX], mix_rate[ZPQ_FAST_MIX], mixbase[ZPQ_FAST_MIX];
 #pragma unroll
       for (int q = 0; q < ZPQ_FAST_MIX; ++q) {
@@ -505,9 +571,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
                   res = clamp2k(sum >> 8);
                 } else {
                   // scalar steps: inputs from the uniform outputs of earlier steps, else from warp A's predictions
-                  int pj = __shfl_sync(FULL, pv, sj);
-#pragma unroll
-                  for (int e = 0; e < ZPQ_FAST_STEPS; ++e) if (e < s && (SIG ? sig7_is_b(SIG, e) : true) && ((srcj[s] >> e) & 1u)) pj = pu[e];
+                  const int pj = __shfl_sync(FULL, pv, sj);                      // owner lanes hold the outputs of earlier steps
                   if (kind == ZK_SSE) {
                     int pq = min(max(pj + 992, 0), 1983);
                     const int wt = pq & 63;
@@ -519,9 +583,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
                     const u32 kk = (u32)pq + (u32)(wt >> 5), vv = (wt >> 5) ? q1 : q0;
                     if (first) { ssek0 = kk; ssev0 = vv; } else { ssek1 = kk; ssev1 = vv; }
                   } else {
-                    int pk = __shfl_sync(FULL, pv, sk & 31);
-#pragma unroll
-                    for (int e = 0; e < ZPQ_FAST_STEPS; ++e) if (e < s && (SIG ? sig7_is_b(SIG, e) : true) && ((srck[s] >> e) & 1u)) pk = pu[e];
+                    const int pk = __shfl_sync(FULL, pv, sk & 31);
                     xjs[s] = pj; xks[s] = pk;
                     if (kind == ZK_MIX2) { const int w = w2u[s]; res = (w * pj + (65536 - w) * pk) >> 16; }
                     else { const int wt = (int)((d >> 19) & 255u); res = (pj * wt + pk * (256 - wt)) >> 8; }       // ZK_AVG
@@ -538,6 +600,8 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
             SEND7(0, y);
             ylast = y;
             // ---- train own components (libzpaq.cpp:1954-2052) ----
+            // squash of every step output at once: an owner lane holds its component's prediction in pv
+            const int sqv = t_squash(S, pv);
 #pragma unroll
             for (int s = 0; s < ZPQ_FAST_STEPS; ++s) {
               const u32 ksig = (u32)((SIG >> (3 * s)) & 7ull);
@@ -547,7 +611,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
                 const int owner = (int)((d >> 3) & 31u);
                 if (kind == ZK_MIX2) {
                   if (lane == owner) {
-                    const int err = ((y * 32767 - t_squash(S, pu[s])) * (int)a4) >> 5;
+                    const int err = ((y * 32767 - sqv) * (int)a4) >> 5;
                     int w = (int)v0;
                     w += (err * (xjs[s] - xks[s]) + (1 << 12)) >> 13;
                     w = min(max(w, 0), 65535);
@@ -568,13 +632,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
 #pragma unroll
             for (int q = 0; q < ZPQ_FAST_MIX; ++q)
               if (q < NMIXC && q < nmix) {
-                int pmq = 0;
-#pragma unroll
-                for (int s = 0; s < ZPQ_FAST_STEPS; ++s) {
-                  const u32 ksig = (u32)((SIG >> (3 * s)) & 7ull);
-                  if (SIG ? (ksig == ZK_MIX && sig7_count(SIG, s, ZK_MIX) == q) : (s < nsteps && (sd[s] & 7u) == ZK_MIX && (int)(sd[s] >> 27) == q)) pmq = pu[s];
-                }
-                const int err = ((y * 32767 - t_squash(S, pmq)) * (int)mix_rate[q]) >> 4;       // warp-uniform
+                const int err = ((y * 32767 - __shfl_sync(FULL, sqv, (int)mix_owner[q])) * (int)mix_rate[q]) >> 4;       // warp-uniform
                 const int w = q == 0 ? mixw0 : (q == 1 ? mixw1 : mixw2);
                 const int x = q == 0 ? mixx0 : (q == 1 ? mixx1 : mixx2);
                 if (lane < (int)mix_m[q]) mix_tab[q][mixbase[q] + lane] = clamp512k(w + ((err * x + (1 << 12)) >> 13));

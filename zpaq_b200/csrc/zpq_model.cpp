@@ -122,7 +122,7 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
   if (prog_len < 1) return fail(err, ZPQ_E_HEADER, "missing HCOMP");
   if (hdr[hlen - 1] != 0) return fail(err, ZPQ_E_HEADER, "missing HCOMP END");
   if (n == 0) return fail(err, ZPQ_E_UNSUPPORTED, "unmodelled (stored) block: not on the context-mixing path");
-  if (n > ZPQ_MAX_LANES) return fail(err, ZPQ_E_UNSUPPORTED, "more than 32 components");
+  const bool wide = n > ZPQ_MAX_LANES;        // more components than lanes: the wide kernel (one thread per block) codes it
   if (hdr[2] > 32) return fail(err, ZPQ_E_COMPONENT, "H too big");
   if (hdr[3] > 32) return fail(err, ZPQ_E_COMPONENT, "M too big");
   if (hdr[2] > 28 || hdr[3] > 31) return fail(err, ZPQ_E_NOMEM, "Out of memory");
@@ -134,19 +134,23 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
 
   Layout lay;
   uint32_t nf = 0;
+  std::vector<ZComp> wcomp(wide ? n : 0);
+  std::vector<ZFill> wfills;
   auto fill = [&](uint32_t off16, uint64_t bytes, uint32_t kind, uint32_t value) -> bool {
+    ZFill f; f.off16 = off16; f.n16 = (uint32_t)((bytes + 15) / 16); f.kind = kind; f.value = value;
+    if (wide) { wfills.push_back(f); ++nf; return true; }
     if (nf >= ZPQ_MAX_FILLS) return false;
-    M->fills[nf].off16 = off16; M->fills[nf].n16 = (uint32_t)((bytes + 15) / 16);
-    M->fills[nf].kind = kind; M->fills[nf].value = value; ++nf;
+    M->fills[nf++] = f;
     return true;
   };
   const uint64_t kMaxTable = (uint64_t)1 << 35;   // 32 GiB per table: beyond any B200 arena
 
-  int ready[ZPQ_MAX_LANES];     // step index after which p[i] is valid (0 = phase A)
+  int ready[256];     // step index after which p[i] is valid (0 = phase A)
   int nsteps = 0;
   const uint8_t* cp = hdr + 7;
   for (int i = 0; i < n; ++i) {
-    ZComp& c = M->comp[i];
+    ZComp& c = wide ? wcomp[i] : M->comp[i];
+    memset(&c, 0, sizeof(c));
     c.type = cp[0];
     c.a1 = cp[1];
     c.a2 = kCompLen[cp[0]] > 2 ? cp[2] : 0;
@@ -260,6 +264,7 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
       case ZT_MIX2: need = std::max(ready[cp[2]], ready[cp[3]]); break;
       default: break;
     }
+    if (wide) { cp += kCompLen[cp[0]]; continue; }      // no step plan: the wide kernel walks the components in order
     if (need >= 0) {
       // first PAR step strictly after `need` (steps are numbered from 1)
       int s = -1;
@@ -292,11 +297,24 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
   // M, H and R are adjacent: one zero fill covers the three (padding included)
   {
     const uint64_t from = M->m_off16, to = (uint64_t)M->r_off16 + 64;
-    if (nf >= ZPQ_MAX_FILLS) return fail(err, ZPQ_E_UNSUPPORTED, "too many tables");
-    M->fills[nf].off16 = (uint32_t)from; M->fills[nf].n16 = (uint32_t)(to - from);
-    M->fills[nf].kind = ZF_ZERO; M->fills[nf].value = 0; ++nf;
+    if (!fill((uint32_t)from, (to - from) * 16, ZF_ZERO, 0)) return fail(err, ZPQ_E_UNSUPPORTED, "too many tables");
+  }
+  if (wide) {
+    M->wst_off16 = lay.alloc((uint64_t)n * 32);
+    fill(M->wst_off16, (uint64_t)n * 32, ZF_ZERO, 0);
   }
   M->nfills = nf;
+  if (wide) {
+    if (lay.pos16 >= ((uint64_t)1 << 32)) return fail(err, ZPQ_E_NOMEM, "Out of memory");
+    M->arena_bytes = ((lay.pos16 * 16) + 255) & ~(uint64_t)255;
+    M->wide = 1;
+    while (image->size() & 15) image->push_back(0);
+    M->wide_comp_off = (uint32_t)image->size();
+    image->insert(image->end(), (const uint8_t*)wcomp.data(), (const uint8_t*)wcomp.data() + wcomp.size() * sizeof(ZComp));
+    M->wide_fill_off = (uint32_t)image->size();
+    image->insert(image->end(), (const uint8_t*)wfills.data(), (const uint8_t*)wfills.data() + wfills.size() * sizeof(ZFill));
+    return ZPQ_OK;
+  }
   const uint32_t ring_off16 = lay.alloc((uint64_t)n * 512);   // prediction rings of the team kernel (never needs init)
   if (lay.pos16 >= ((uint64_t)1 << 32)) return fail(err, ZPQ_E_NOMEM, "Out of memory");
   M->arena_bytes = ((lay.pos16 * 16) + 255) & ~(uint64_t)255;
