@@ -176,6 +176,7 @@ typedef struct SimtStream* cudaStream_t;
 typedef struct SimtEvent* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaStreamNonBlocking = 1 };
+enum { cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp {
   char name[256];
@@ -195,6 +196,8 @@ cudaError_t cudaStreamDestroy(cudaStream_t st);
 cudaError_t cudaStreamSynchronize(cudaStream_t st);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaEventCreate(cudaEvent_t* e);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags);
+cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned flags);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);

@@ -61,6 +61,8 @@ struct zpq_ctx {
   void* ws = nullptr; uint64_t ws_bytes = 0; bool own_ws = true;
   DevBuf d_in, d_out, d_meta, d_pbuf, d_cstate, d_prep, d_stage_in, d_stage_out;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};      // side streams for concurrent decoder launches of different step signatures
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   std::string err;
   float ms[3] = {0, 0, 0};
   float ms_prep = 0;           // device time of the last analysis pass (SHA-1, gap statistics); added to ms[0] by the whole-block calls
@@ -188,9 +190,13 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
       return Mi.fast.ok ? 3 : 4;
     };
     // class first, then model: the wavefront encoder wants 32 blocks of one model per warp
+    // (inside the step-plan class: by step signature, so that every signature gets the kernel instantiated for it)
+    auto sig_of = [&](int i) -> unsigned long long { return zpq_code2_signature(&models[jobs[i].model].fast); };
     std::stable_sort(wave.begin(), wave.end(), [&](int a, int b) {
       const int ca = kclass(a), cb = kclass(b);
-      return ca != cb ? ca < cb : jobs[a].model < jobs[b].model;
+      if (ca != cb) return ca < cb;
+      if (ca == 3) { const unsigned long long sa = sig_of(a), sb = sig_of(b); if (sa != sb) return sa < sb; }
+      return jobs[a].model < jobs[b].model;
     });
     int ncls[6] = {0, 0, 0, 0, 0, 0};
     for (int i : wave) ++ncls[kclass(i)];
@@ -351,6 +357,30 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
           }
         }
         else {
+          // Runs of one step signature are launched side by side on auxiliary streams (a launch is bound by the latency
+          // of its longest block, not by the number of blocks: one after the other would multiply that time).
+          std::vector<std::pair<int, int>> runs;
+          for (int k = first; k < first + cnt;) {
+            int e = k + 1;
+            while (e < first + cnt && sig_of(wave[e]) == sig_of(wave[k])) ++e;
+            runs.push_back(std::make_pair(k, e - k));
+            k = e;
+          }
+          const int first_all = first, cnt_all = cnt;
+          for (size_t rix = 0; rix < runs.size(); ++rix) {
+          const int first = runs[rix].first, cnt = runs[rix].second;
+          ZKernelArgs Ak = A;
+          Ak.blocks = A.blocks + first; Ak.status = A.status + first; Ak.out_len = A.out_len + first;
+          Ak.counter = A.counter + 8 + (rix % 48); Ak.nblk = cnt;
+          cudaStream_t st = ctx->stream;
+          if (rix > 0 && runs.size() > 1) {
+            const int ax = (int)((rix - 1) % 3);
+            if (!ctx->aux[ax]) CK(cudaStreamCreateWithFlags(&ctx->aux[ax], cudaStreamNonBlocking), "aux stream");
+            if (!ctx->ev_fork) { CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming), "event"); }
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream), "event");
+            st = ctx->aux[ax];
+            CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0), "fork");
+          }
           // one CTA per SM; W blocks in flight share the 227 KB carve-out
           uint32_t pw = 16;
           for (int k = first; k < first + cnt; ++k) pw = std::max(pw, models[jobs[wave[k]].model].fast.pw_bytes);
@@ -385,6 +415,13 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
             }
           }
           ++ctx->launches;
+          if (st != ctx->stream) {
+            if (!ctx->ev_join[rix % 3]) CK(cudaEventCreateWithFlags(&ctx->ev_join[rix % 3], cudaEventDisableTiming), "event");
+            CK(cudaEventRecord(ctx->ev_join[rix % 3], st), "event");
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[rix % 3], 0), "join");
+          }
+          }
+          (void)first_all; (void)cnt_all;
         }
         first += cnt;
       }
@@ -500,7 +537,7 @@ int zpq_create(int device, zpq_ctx** out) {
   ctx->device = device;
   if (const char* gs = getenv("ZPQ_GROUP")) { const int v = atoi(gs); if (v >= 1 && v <= 32) ctx->wave_group = v; }
   if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
-  if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 31) ctx->wave_variant = v; }
+  if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 63) ctx->wave_variant = v; }
   if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if ((v >= 0 && v <= 3) || v == 7 || v == 15 || v == 31) ctx->dec_variant = v; }
   if (const char* dk = getenv("ZPQ_DEC_KERNEL")) { const int v = atoi(dk); if (v == 6 || v == 7) ctx->dec_kernel = v; }
   if (const char* wo = getenv("ZPQ_WAVE_ORDER")) ctx->wave_role_major = atoi(wo) != 0;
@@ -529,6 +566,8 @@ void zpq_destroy(zpq_ctx* ctx) {
   if (ctx->own_ws && ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 3; ++i) { if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -52,7 +52,7 @@ __device__ __forceinline__ void enc5_bit(Enc5& C, int y, u32 p16) {
 // ROLE 0: component threads and MIX warps in one launch; 1: component threads only; 2: MIX warps only
 // (the split launches have their own register budgets).  Returns the profiling slot of the warp
 // (component type, 10 = coder, 11 + q = mixer q) or -1 for a warp without work in this wave.
-template <int ROLE, bool MIXPF>
+template <int ROLE, bool MIXPF, int UNR>
 __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem) {
   const Tabs S = make_tabs(smem);
   const ZKernelArgs& A = W.A;
@@ -229,7 +229,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
           if (isse) prefetch_l1(&pb[PBIDX(a2, slot, i + 1)]);
         }
         uint4 vout = make_uint4(0, 0, 0, 0);
-#pragma unroll
+#pragma unroll UNR
         for (int nb = 0; nb < 2; ++nb) {
           if (nb == 1) {
             const u64 hs = (hist << 8) | (u64)cur;
@@ -341,7 +341,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
           key = rb + (u32)(min(max(vget(vin_j, 0) + 992, 0), 1983) >> 6);
           q0 = gtab[key]; q1 = gtab[key + 1u];
         }
-#pragma unroll
+#pragma unroll (UNR == 2 ? 8 : 2)
         for (int bit = 0; bit < 8; ++bit) {
           const int y = (int)((cur >> (7 - bit)) & 1u);
           if ((bit & 3) == 0) {
@@ -830,13 +830,13 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
   return -1;
 }
 
-template <int ROLE, bool MIXPF>
+template <int ROLE, bool MIXPF, int UNR>
 __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
   extern __shared__ __align__(16) unsigned char smem[];
   stage_tables(smem, W.A.tables);
   __syncthreads();
   const long long t0 = W.prof ? clock64() : 0;
-  const int slot = wave_body<ROLE, MIXPF>(W, smem);
+  const int slot = wave_body<ROLE, MIXPF, UNR>(W, smem);
   if (W.prof && slot >= 0) {
     if ((threadIdx.x & 31) == 0) { atomicAdd(W.prof + 2 * slot, (unsigned long long)(clock64() - t0)); atomicAdd(W.prof + 2 * slot + 1, 1ull); }
   }
@@ -845,20 +845,30 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
 // ---------------------------------------------------------------------------
 extern "C" cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant) {
   // variant bit 0: byte-ahead weight rows in the MIX warps; bit 1: component threads and MIX warps as two launches
-  // (w->mix_threads: the mixers are component threads, there are no MIX warps to launch)
+  // (w->mix_threads: the mixers are component threads, there are no MIX warps to launch); bit 5: compact code (the
+  // nibble loop of the ICM / ISSE threads rolled, the SSE byte loop unrolled by two instead of eight): the fully unrolled
+  // kernel is 190 KB of SASS, more than an SM's instruction cache once every role is resident
   const int wa = w->ngroups * w->ncs, wm = w->mix_threads ? 0 : w->A.nblk * ZPQ_FAST_MIX;
   if (wa + wm <= 0) return cudaSuccess;
-  const bool pf = (variant & 1) != 0;
+  const bool pf = (variant & 1) != 0, compact = (variant & 32) != 0;
   if (variant & 2) {
-    if (wa > 0) zpq_wave_kernel<1, false><<<(wa + 3) / 4, 128, S2_STATIC, st>>>(*w);
+    if (wa > 0) {
+      if (compact) zpq_wave_kernel<1, false, 1><<<(wa + 3) / 4, 128, S2_STATIC, st>>>(*w);
+      else zpq_wave_kernel<1, false, 2><<<(wa + 3) / 4, 128, S2_STATIC, st>>>(*w);
+    }
     if (wm > 0) {
-      if (pf) zpq_wave_kernel<2, true><<<(wm + 3) / 4, 128, S2_STATIC, st>>>(*w);
-      else zpq_wave_kernel<2, false><<<(wm + 3) / 4, 128, S2_STATIC, st>>>(*w);
+      if (pf) zpq_wave_kernel<2, true, 2><<<(wm + 3) / 4, 128, S2_STATIC, st>>>(*w);
+      else zpq_wave_kernel<2, false, 2><<<(wm + 3) / 4, 128, S2_STATIC, st>>>(*w);
     }
   } else {
     const int ctas = (wa + wm + 3) / 4;
-    if (pf) zpq_wave_kernel<0, true><<<ctas, 128, S2_STATIC, st>>>(*w);
-    else zpq_wave_kernel<0, false><<<ctas, 128, S2_STATIC, st>>>(*w);
+    if (compact) {
+      if (pf) zpq_wave_kernel<0, true, 1><<<ctas, 128, S2_STATIC, st>>>(*w);
+      else zpq_wave_kernel<0, false, 1><<<ctas, 128, S2_STATIC, st>>>(*w);
+    } else {
+      if (pf) zpq_wave_kernel<0, true, 2><<<ctas, 128, S2_STATIC, st>>>(*w);
+      else zpq_wave_kernel<0, false, 2><<<ctas, 128, S2_STATIC, st>>>(*w);
+    }
   }
   return cudaGetLastError();
 }
