@@ -66,8 +66,9 @@ def test_kernel_variants_are_bit_exact(env, values):
 
 @pytest.mark.timeout(1500)
 def test_full_size_mixed_models_in_one_launch(ctx):
-    """BASELINE-size blocks (1 044 480 B), >= 256 of them, FIVE different models in ONE launch: level 5 on text (27
-    components: the period model fires), on 'mixed' and on random bytes (23), level 4 on text (8) and the 17-component chain.
+    """BASELINE-size blocks (1 044 480 B), >= 256 of them, FOUR different models (three step signatures) in ONE batch: level 5
+    on text (27 components: the period model fires), on 'mixed' and on random bytes (23), level 4 on text (8) and the
+    17-component chain.
     One block of every model is compared with the oracle byte for byte; every block must decode back to its input."""
     n = (1 << 20) - 4096
     plan = [("5", 0, 64), ("5", 1, 64), ("5", 2, 48), ("4", 0, 48), (CFG_ALL_METHOD, 1, 40)]
@@ -78,7 +79,7 @@ def test_full_size_mixed_models_in_one_launch(ctx):
             p = O.gen_block(kind, 9000 + 97 * kind + i, n)
             hdrs.append(Z.model_from_method(method, p))
             datas.append(b"\0" + p)
-    assert len(datas) >= 256 and len(set(hdrs)) >= 5
+    assert len(datas) >= 256 and len(set(hdrs)) >= 4
     assert hdrs[first[0]][6] == 27 and hdrs[first[1]][6] == 23
     enc = ctx.encode_blocks(hdrs, datas)
     assert all(st == 0 for st, _ in enc)

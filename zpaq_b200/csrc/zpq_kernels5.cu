@@ -193,7 +193,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
         }
         pb[PBIDX(c, slot, i)] = vout;
         const u64 hs = (hist << 8) | (u64)cur;
-        h = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, 0u);
+        h = wave_hash<UNR == 1>(fold1, fops, flen, st, cur, hs, pos, in, 0u);
         hist = hs;
         if (pos + 1 < b1) {                      // the next byte's eight rows are known now: pull them towards L2
           const u32 nxt = in[pos + 1];
@@ -234,7 +234,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
           if (nb == 1) {
             const u64 hs = (hist << 8) | (u64)cur;
             if (cur == dist_byte) dist_last = (u32)(-(pos + 1));
-            h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
+            h_next = wave_hash<UNR == 1>(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
             hist = hs;
           }
           // Predictor::find (libzpaq.cpp:2072-2088) on rows requested one nibble ago
@@ -352,7 +352,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
             if (bit == 4) {
               const u64 hs = (hist << 8) | (u64)cur;
               if (cur == dist_byte) dist_last = (u32)(-(pos + 1));
-              h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
+              h_next = wave_hash<UNR == 1>(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
               hist = hs;
             }
           }
@@ -445,7 +445,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
           if (bit == 4) {
             const u64 hs = (hist << 8) | (u64)cur;
             if (cur == dist_byte) dist_last = (u32)(-(pos + 1));
-            h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
+            h_next = wave_hash<UNR == 1>(fold1, fops, flen, st, cur, hs, pos, in, dist_last);
             hist = hs;
           }
           if (is_hash) {
@@ -695,7 +695,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
         }
         // the next byte's hash needs only input data: evaluate it now and pull the next byte's rows towards L2
         const u64 hs = (hist << 8) | (u64)cur;
-        h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, 0u);
+        h_next = wave_hash<UNR == 1>(fold1, fops, flen, st, cur, hs, pos, in, 0u);
         hist = hs;
         if (more && lane < 16) {
           const int* const r = tab + ((h_next + (((0x100u | cur_n) >> (8 - kk)) & a5)) & cmm) * (u32)m;
@@ -751,7 +751,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
         for (int bit = 0; bit < 8; ++bit) {
           if (bit == 4) {
             const u64 hs = (hist << 8) | (u64)cur;
-            h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, 0u);
+            h_next = wave_hash<UNR == 1>(fold1, fops, flen, st, cur, hs, pos, in, 0u);
             hist = hs;
             if (more) {
               latem = 0u;
@@ -789,7 +789,7 @@ __device__ __forceinline__ int wave_body(const ZWaveArgs& W, unsigned char* smem
       for (int bit = 0; bit < 8; ++bit) {
         if (bit == 4) {
           const u64 hs = (hist << 8) | (u64)cur;
-          h_next = wave_hash(fold1, fops, flen, st, cur, hs, pos, in, 0u);
+          h_next = wave_hash<UNR == 1>(fold1, fops, flen, st, cur, hs, pos, in, 0u);
           hist = hs;
         }
         const u32 c8 = (0x100u | cur) >> (8 - bit);
@@ -846,8 +846,12 @@ __global__ void __launch_bounds__(128) zpq_wave_kernel(const ZWaveArgs W) {
 extern "C" cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant) {
   // variant bit 0: byte-ahead weight rows in the MIX warps; bit 1: component threads and MIX warps as two launches
   // (w->mix_threads: the mixers are component threads, there are no MIX warps to launch); bit 5: compact code (the
-  // nibble loop of the ICM / ISSE threads rolled, the SSE byte loop unrolled by two instead of eight): the fully unrolled
-  // kernel is 190 KB of SASS, more than an SM's instruction cache once every role is resident
+  // nibble loop of the ICM / ISSE threads rolled, the SSE byte loop unrolled by two instead of eight).  The fully unrolled
+  // kernel is 190 KB of SASS and every role is resident on every SM: ncu showed 7 of 19.6 stall cycles per instruction
+  // waiting for instruction fetch (profiles/r02a_wave_*).  The smallest hot code -- one generic per-bit loop for all
+  // component threads (no bit 4) plus the byte-batched MIX warps -- measured fastest (profiles/r02e_session.log);
+  // a single non-inlined copy of the recipe interpreter removed the fetch stalls altogether (0.4 cycles) but cost more
+  // in spills around the call and extra instructions than it saved (profiles/r02f_*), so the interpreter stays inlined
   const int wa = w->ngroups * w->ncs, wm = w->mix_threads ? 0 : w->A.nblk * ZPQ_FAST_MIX;
   if (wa + wm <= 0) return cudaSuccess;
   const bool pf = (variant & 1) != 0, compact = (variant & 32) != 0;
