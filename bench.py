@@ -585,9 +585,15 @@ def main():
         # dominant kernels = the coding kernels of the two directions (per rank)
         per_rank_alg = nbytes * done * balg * 2          # both directions touch the same tables
         achieved = per_rank_alg / (code_c + code_d) / 1e9
-        traffic = None
+        # DRAM traffic of the two coding kernels from their ncu captures (bytes per input byte, profiles/r02_traffic.json),
+        # scaled to what this rank coded: the same "per launch set" basis as `achieved`
+        traffic = traffic_detail = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            traffic_detail = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if cfg == "m5_1g":
+                traffic = nbytes * done * (traffic_detail["encode_bytes_per_input_byte"] + traffic_detail["decode_bytes_per_input_byte"]) / (code_c + code_d) / 1e9
+            else:
+                traffic_detail = {"note": "ncu captures are of the -method 5 chain (profiles/r02_traffic.json); not measured for this configuration"}
         except Exception:
             pass
         # bit-exactness against the CPU reference on a bounded sample, and the CPU baseline itself
@@ -626,7 +632,8 @@ def main():
                     "h2d_bytes_per_step": int(nbytes + r["arc_bytes"]), "d2h_bytes_per_step": int(r["arc_bytes"] + nbytes)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_unit": "GB/s of DRAM traffic (ncu dram__bytes per input byte x bytes coded / kernel time)",
+                         "traffic_detail": traffic_detail, "peak_source": peak_src,
                          "alg_bytes_per_input_byte": balg,
                          "encode": {"achieved": nbytes * done * balg / code_c / 1e9, "frac": nbytes * done * balg / code_c / 1e9 / peak},
                          "decode": {"achieved": nbytes * done * balg / code_d / 1e9, "frac": nbytes * done * balg / code_d / 1e9 / peak},
