@@ -70,7 +70,7 @@ struct zpq_ctx {
   uint32_t tiers[6] = {0, 0, 0, 0, 0, 0};   // blocks of the last batch per kernel tier (zpq_last_tiers)
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 512;        // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two; 512 measured best in round 2: profiles/r02c)
-  int wave_variant = 41;       // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps, bit 4 nibble-unrolled ICM / ISSE / SSE loops, bit 5 compact code (less unrolling); 41 = the smallest hot code, measured fastest in round 2
+  int wave_variant = 57;       // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps, bit 4 ICM / ISSE / SSE threads in their own nibble / byte loops, bit 5 compact code (nibble loop rolled, SSE loop unrolled by 2, compact inlined recipe interpreter); 57 measured fastest at the benchmark's size (profiles/r02h_session.log)
   int dec_variant = 31;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7 or 15) slot-scheduled hashes, bit 3 (15) MATCH in warp A, bit 4 (31) register-resident predictions in warp B
   int wave_role_major = 1;     // ZPQ_WAVE_ORDER: 1 = role-major warp order of the wavefront encoder (default), 0 = group-major (round 1)
   bool wave_prof = false;      // ZPQ_WAVE_PROF=1: per-role warp cycles of the wavefront encoder to stderr
