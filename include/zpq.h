@@ -128,8 +128,9 @@ int zpq_last_timing(const zpq_ctx* ctx, float ms[3]);
 uint64_t zpq_launch_count(const zpq_ctx* ctx);
 /* Diagnostics: blocks of the last batch coded by each kernel tier: [0] wavefront encoder (zpq_kernels5.cu),
  * [1] critical-first two-warp decoder (zpq_kernels7.cu), [2] round-1 two-warp decoder (zpq_kernels6.cu),
- * [3] one-warp fast kernel (zpq_kernels2.cu), [4] generic kernel (zpq_kernels.cu), [5] wide generic kernel (n > 32). */
-int zpq_last_tiers(const zpq_ctx* ctx, uint32_t tiers[6]);
+ * [3] one-warp fast kernel (zpq_kernels2.cu), [4] generic kernel (zpq_kernels.cu), [5] wide generic kernel (n > 32),
+ * [6] lock-step decoder with lanes = blocks (zpq_kernels8.cu). */
+int zpq_last_tiers(const zpq_ctx* ctx, uint32_t tiers[7]);
 
 /* ---- whole blocks (framing kept from the reference, host side) ------------ */
 /* Batched libzpaq::compressBlock (libzpaq.cpp:7543-7731): for each payload

@@ -35,10 +35,11 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(scope="session", params=["5", "5/dec6", "2", "1"], ids=["production", "dec6", "fast", "generic"])
+@pytest.fixture(scope="session", params=["5", "5/dec6", "5/dec8", "2", "1"], ids=["production", "dec6", "dec8", "fast", "generic"])
 def kctx(request):
     """Every kernel tier: 5 = production (wavefront encoder + critical-first two-warp decoder zpq_kernels7.cu), 5/dec6 = the
-    round-1 two-warp decoder (generic step lists fall back to it), 2 = one-warp kernel for both directions, 1 = generic kernel."""
+    round-1 two-warp decoder (generic step lists fall back to it), 5/dec8 = the opt-in lock-step decoder with lanes = blocks
+    (zpq_kernels8.cu), 2 = one-warp kernel for both directions, 1 = generic kernel."""
     k, _, d = request.param.partition("/dec")
     c = _make_ctx(k, d or "7")
     yield c

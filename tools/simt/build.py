@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "zpaq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
-CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_prep.cu", "zpq_abi.cu"]
+CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_kernels8.cu", "zpq_prep.cu", "zpq_abi.cu"]
 CPP = ["zpq_model.cpp", "zpq_method.cpp", "zpq_frame.cpp", "zpq_hcomp.cpp"]
 
 
@@ -53,8 +53,8 @@ def translate(text, name):
         return "simt_launch(dim3(%s), dim3(%s), (size_t)(%s), [&]() { %s(%s); });" % (cfg[0], cfg[1], cfg[2], m.group(1), m.group(3))
     text, n_launch = LAUNCH.subn(launch, text)
     text, n_smem = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];", r"unsigned char* \1 = simt_dyn_smem();", text)
-    text, n_bar = re.subn(r'asm volatile\("bar\.sync %0, %1;"\s*::\s*"r"\((.*?)\),\s*"r"\((\d+)\)\s*:\s*"memory"\)', r"simt_named_barrier(\1, \2)", text)
-    text, n_arr = re.subn(r'asm volatile\("bar\.arrive %0, %1;"\s*::\s*"r"\((.*?)\),\s*"r"\((\d+)\)\s*:\s*"memory"\)', r"simt_named_arrive(\1, \2)", text)
+    text, n_bar = re.subn(r'asm volatile\("bar\.sync %0, %1;"\s*::\s*"r"\((.*?)\),\s*"r"\((\w+)\)\s*:\s*"memory"\)', r"simt_named_barrier(\1, \2)", text)
+    text, n_arr = re.subn(r'asm volatile\("bar\.arrive %0, %1;"\s*::\s*"r"\((.*?)\),\s*"r"\((\w+)\)\s*:\s*"memory"\)', r"simt_named_arrive(\1, \2)", text)
     n_bar += n_arr
     text, n_pf = re.subn(r'asm volatile\("prefetch\.global\.L[12] \[%0\];"\s*::\s*"l"\((\w+)\)\)', r"(void)(\1)", text)
     text, n_spin = re.subn(r"(while \(.*\)) \{ \}", r"\1 { simt_spin(); }", text)

@@ -187,9 +187,9 @@ class Context:
 
     def tiers(self):
         """Blocks of the last batch per kernel tier (zpq_last_tiers): wave encoder, dec7, dec6, fast, generic, wide generic."""
-        t = (C.c_uint32 * 6)()
+        t = (C.c_uint32 * 7)()
         lib().zpq_last_tiers(self._h, t)
-        return dict(zip(("wave_enc", "dec7", "dec6", "fast", "generic", "wide"), [int(x) for x in t]))
+        return dict(zip(("wave_enc", "dec7", "dec6", "fast", "generic", "wide", "dec8"), [int(x) for x in t]))
 
     def launch_count(self):
         return int(lib().zpq_launch_count(self._h))

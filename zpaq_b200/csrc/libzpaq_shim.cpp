@@ -54,6 +54,10 @@ struct Req {
   std::vector<uint8_t> out; uint64_t out_len = 0; int status = 1; bool done = false;
 };
 
+// how long the submitter waits for more blocks before it launches (zpaq keeps at most `-threads` blocks in flight, and a
+// launch is bound by the latency of one block, so waiting a few milliseconds for all of them costs nothing): ZPQ_SHIM_WINDOW_MS
+int window_ms() { static const int ms = [] { const char* e = getenv("ZPQ_SHIM_WINDOW_MS"); const int v = e ? atoi(e) : 2; return v < 0 ? 0 : (v > 1000 ? 1000 : v); }(); return ms; }
+
 struct Batcher {
   std::mutex mu; std::condition_variable cv_submit, cv_done;
   std::vector<Req*> queue;
@@ -69,7 +73,7 @@ struct Batcher {
         // give concurrently running compress threads a moment to add their blocks (zpaq keeps
         // `threads` blocks in flight), then take everything that is queued
         lk.unlock();
-        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        std::this_thread::sleep_for(std::chrono::milliseconds(window_ms()));
         lk.lock();
         batch.swap(queue);
       }

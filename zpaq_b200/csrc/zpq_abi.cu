@@ -59,7 +59,7 @@ struct zpq_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   ZTables* d_tables = nullptr;
   void* ws = nullptr; uint64_t ws_bytes = 0; bool own_ws = true;
-  DevBuf d_in, d_out, d_meta, d_pbuf, d_cstate, d_prep, d_stage_in, d_stage_out;
+  DevBuf d_in, d_out, d_meta, d_pbuf, d_cstate, d_prep, d_stage_in, d_stage_out, d_groups[4];
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};      // side streams for concurrent decoder launches of different step signatures
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
@@ -67,14 +67,14 @@ struct zpq_ctx {
   float ms[3] = {0, 0, 0};
   float ms_prep = 0;           // device time of the last analysis pass (SHA-1, gap statistics); added to ms[0] by the whole-block calls
   uint64_t launches = 0;
-  uint32_t tiers[6] = {0, 0, 0, 0, 0, 0};   // blocks of the last batch per kernel tier (zpq_last_tiers)
+  uint32_t tiers[7] = {0, 0, 0, 0, 0, 0, 0};   // blocks of the last batch per kernel tier (zpq_last_tiers)
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
   int wave_chunk = 512;        // bytes per wave of the wavefront encoder (ZPQ_CHUNK overrides; power of two; 512 measured best in round 2: profiles/r02c)
   int wave_variant = 57;       // ZPQ_WAVE_VARIANT: bit 0 byte-ahead MIX rows, bit 1 component threads / MIX warps as two launches, bit 2 mixers as component threads, bit 3 byte-batched MIX warps, bit 4 ICM / ISSE / SSE threads in their own nibble / byte loops, bit 5 compact code (nibble loop rolled, SSE loop unrolled by 2, compact inlined recipe interpreter); 57 measured fastest at the benchmark's size (profiles/r02h_session.log)
   int dec_variant = 31;         // ZPQ_DEC_VARIANT: bit 0 CM in warp A with candidate entries, bit 1 candidate MIX / SSE rows in warp B, bit 2 (only as 7 or 15) slot-scheduled hashes, bit 3 (15) MATCH in warp A, bit 4 (31) register-resident predictions in warp B
   int wave_role_major = 1;     // ZPQ_WAVE_ORDER: 1 = role-major warp order of the wavefront encoder (default), 0 = group-major (round 1)
   bool wave_prof = false;      // ZPQ_WAVE_PROF=1: per-role warp cycles of the wavefront encoder to stderr
-  int dec_kernel = 7;           // ZPQ_DEC_KERNEL: 7 = critical-first two-warp decoder (zpq_kernels7.cu), 6 = round-1 two-warp decoder
+  int dec_kernel = 7;           // ZPQ_DEC_KERNEL: 7 = critical-first two-warp decoder (zpq_kernels7.cu, default), 6 = round-1 two-warp decoder, 8 = lock-step decoder with lanes = blocks (zpq_kernels8.cu: correct, measured 2-3x slower, opt-in)
   int kernel_version = 5;      // ZPQ_KERNEL caps the kernel tier: 1 generic, 2 one-warp fast kernel, 5 production (wavefront encoder, two-warp decoder)
 };
 
@@ -96,7 +96,7 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
   if (!ctx) return ZPQ_E_ARG;
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   ctx->ms[0] = ctx->ms[1] = ctx->ms[2] = 0;
-  for (int t = 0; t < 6; ++t) ctx->tiers[t] = 0;
+  for (int t = 0; t < 7; ++t) ctx->tiers[t] = 0;
   const int nj = (int)jobs.size();
   if (nj == 0) return ZPQ_OK;
   const auto t_begin = std::chrono::steady_clock::now();
@@ -395,7 +395,32 @@ int run_batch(zpq_ctx* ctx, std::vector<IJob>& jobs, bool decode, bool dev_io) {
               for (int k = first; k < first + cnt && pair; ++k) pair = models[jobs[wave[k]].model].fast.pair_ok != 0;
               bool hp_all = true;
               for (int k = first; k < first + cnt; ++k) if (!models[jobs[wave[k]].model].hplan.ok) { hp_all = false; break; }
-              if (pair && hp_all && ctx->dec_kernel >= 7 && zpq_dec7_takes(sig)) {
+              bool tp_all = decode && kv >= 5 && ctx->dec_kernel >= 8;
+              uint32_t nh_max = 0;
+              for (int k = first; k < first + cnt && tp_all; ++k) {
+                const ZModel& Mk = models[jobs[wave[k]].model];
+                tp_all = Mk.tplan.ok != 0; nh_max = std::max(nh_max, Mk.tplan.nh);
+              }
+              if (tp_all) {
+                // lanes = blocks: one CTA decodes up to eight blocks of one model in lock step (zpq_kernels8.cu)
+                const uint64_t room8 = ZPQ_SMEM_MAX - (uint64_t)zpq_dec8_static_smem() - (uint64_t)zpq_dec8_xchg_bytes();
+                const int nbk = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, room8 / pw));
+                std::vector<uint32_t> gf, gc;
+                for (int k = first; k < first + cnt; ++k) {
+                  if (gf.empty() || jobs[wave[k]].model != jobs[wave[k - 1]].model || (int)gc.back() == nbk) { gf.push_back((uint32_t)(k - first)); gc.push_back(0); }
+                  ++gc.back();
+                }
+                const int ng = (int)gf.size();
+                DevBuf& gb = ctx->d_groups[rix % 4];
+                CK(gb.reserve((uint64_t)ng * 8 + 64), "group table cudaMalloc");
+                CK(cudaMemcpyAsync(gb.p, gf.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, st), "H2D groups");
+                CK(cudaMemcpyAsync((uint8_t*)gb.p + (size_t)ng * 4, gc.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, st), "H2D groups");
+                CK(cudaStreamSynchronize(st), "groups");          // the host vectors go out of scope
+                CK(zpq_launch_dec8(&Ak, (const uint32_t*)gb.p, (const uint32_t*)((uint8_t*)gb.p + (size_t)ng * 4), ng, nbk, (int)pw,
+                                   (int)nh_max + 4, ctx->sm_count, st), "zpq_dec_kernel8 launch");
+                ctx->tiers[6] += (uint32_t)cnt;
+              }
+              else if (pair && hp_all && ctx->dec_kernel >= 7 && zpq_dec7_takes(sig)) {
                 // two warps per block, critical-first ordering (zpq_kernels7.cu)
                 const uint64_t room7 = ZPQ_SMEM_MAX - (uint64_t)zpq_dec7_static_smem();
                 const int teams = (int)std::max<uint64_t>(1, std::min<uint64_t>(7, room7 / (pw + (uint64_t)zpq_dec7_ctrl_bytes())));
@@ -539,7 +564,7 @@ int zpq_create(int device, zpq_ctx** out) {
   if (const char* cb = getenv("ZPQ_CHUNK")) { const int v = atoi(cb); if (v >= 128 && v <= 65536 && (v & (v - 1)) == 0) ctx->wave_chunk = v; }
   if (const char* wv = getenv("ZPQ_WAVE_VARIANT")) { const int v = atoi(wv); if (v >= 0 && v <= 63) ctx->wave_variant = v; }
   if (const char* dv = getenv("ZPQ_DEC_VARIANT")) { const int v = atoi(dv); if ((v >= 0 && v <= 3) || v == 7 || v == 15 || v == 31) ctx->dec_variant = v; }
-  if (const char* dk = getenv("ZPQ_DEC_KERNEL")) { const int v = atoi(dk); if (v == 6 || v == 7) ctx->dec_kernel = v; }
+  if (const char* dk = getenv("ZPQ_DEC_KERNEL")) { const int v = atoi(dk); if (v >= 6 && v <= 8) ctx->dec_kernel = v; }
   if (const char* wo = getenv("ZPQ_WAVE_ORDER")) ctx->wave_role_major = atoi(wo) != 0;
   if (const char* wp = getenv("ZPQ_WAVE_PROF")) ctx->wave_prof = atoi(wp) != 0;
   if (const char* kv = getenv("ZPQ_KERNEL")) { const int v = atoi(kv); if (v >= 1 && v <= 5) ctx->kernel_version = v; }
@@ -562,7 +587,7 @@ void zpq_destroy(zpq_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release(); ctx->d_prep.release(); ctx->d_stage_in.release(); ctx->d_stage_out.release();
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release(); ctx->d_prep.release(); ctx->d_stage_in.release(); ctx->d_stage_out.release(); for (int i = 0; i < 4; ++i) ctx->d_groups[i].release();
   if (ctx->own_ws && ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -651,9 +676,9 @@ int zpq_last_timing(const zpq_ctx* ctx, float ms[3]) {
 
 uint64_t zpq_launch_count(const zpq_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int zpq_last_tiers(const zpq_ctx* ctx, uint32_t tiers[6]) {
+int zpq_last_tiers(const zpq_ctx* ctx, uint32_t tiers[7]) {
   if (!ctx || !tiers) return ZPQ_E_ARG;
-  for (int t = 0; t < 6; ++t) tiers[t] = ctx->tiers[t];
+  for (int t = 0; t < 7; ++t) tiers[t] = ctx->tiers[t];
   return ZPQ_OK;
 }
 

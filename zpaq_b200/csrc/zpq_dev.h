@@ -186,6 +186,23 @@ struct ZTeam {
   uint8_t comp_at[ZPQ_ROLES][32];        // role 0 / 2: lane -> component (0xff: idle lane)
 };
 
+// Lock-step decode plan (zpq_kernels8.cu): lane = block, one warp per ICM / ISSE component, one warp for up to four
+// CM / MATCH / CONST components, one for the ISSE chains, one for the mixers, one for the scalar steps and the decoders.
+#define ZPQ_T_HASH 24
+#define ZPQ_T_MISC 4
+#define ZPQ_T_SCALAR 4
+struct ZTPlan {
+  uint32_t ok;
+  uint32_t nh;                         // hash warps
+  uint32_t nmisc, nisse, nscalar;
+  uint8_t hcomp[ZPQ_T_HASH];           // component of hash warp k
+  uint8_t mcomp[ZPQ_T_MISC];           // CM / MATCH / CONST components (slots of the misc warp)
+  uint8_t icomp[ZPQ_T_HASH];           // ISSE components in component order
+  uint8_t ijn[ZPQ_T_HASH];             // their input components
+  uint8_t isse_ord[ZPQ_MAX_LANES];     // component -> index in icomp
+  uint8_t scomp[ZPQ_T_SCALAR];         // MIX2 / SSE / AVG components in component order
+};
+
 struct ZModel {
   uint32_t n, hh, hm;
   uint32_t prog_off;      // offset of the guarded program image in the program pool
@@ -214,6 +231,8 @@ struct ZModel {
   ZRecipes rcp;
   // ---- slot-scheduled hashes for the two-warp decoder (zpq_kernels6.cu) ----
   ZHashPlan hplan;
+  // ---- lock-step decoder (zpq_kernels8.cu) ----
+  ZTPlan tplan;
 };
 
 struct ZBlock {

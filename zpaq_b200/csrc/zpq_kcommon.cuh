@@ -157,14 +157,14 @@ __device__ __forceinline__ u32 flat_eval(const u32* __restrict__ ops, u32 len, u
 // The same interpreter with one op per iteration and no unrolling: a quarter of the code of flat_eval (which is inlined
 // at every call site of every role of the wavefront encoder; the instruction caches of an SM hold all resident roles).
 __device__ __forceinline__ u32 flat_eval_compact(const u32* __restrict__ ops, u32 len, u32 st[ZPQ_FLAT_SEGS], u32 cur, u64 hs,
-                                                 int bpos, const u8* in, u32 dist_last) {
+                                                 int bpos, const u8* in, u32 dist_last, u32 ring_mask = 0) {
   const u32 vc = (u32)(-(bpos + 1));
   FlatState F; F.acc = 0; F.prev_new = 0; F.prev_old = 0; F.k = -1; F.skip = false; F.w_pending = 0;
   u32 w = len ? __ldg(ops) : 0u;
 #pragma unroll 1
   for (u32 t = 0; t < len; ++t) {
     const u32 wn = (t + 1 < len) ? __ldg(ops + t + 1) : 0u;
-    flat_op(F, w, wn, st, cur, hs, bpos, in, dist_last, vc, 0);
+    flat_op(F, w, wn, st, cur, hs, bpos, in, dist_last, vc, ring_mask);
     w = wn;
   }
   if (F.k == 0) st[0] = F.acc; else if (F.k == 1) st[1] = F.acc; else if (F.k == 2) st[2] = F.acc; else if (F.k == 3) st[3] = F.acc;

@@ -23,6 +23,10 @@ int zpq_dec7_static_smem(void);
 int zpq_dec7_ctrl_bytes(void);
 int zpq_dec7_takes(unsigned long long sig);
 cudaError_t zpq_launch_dec7(const ZKernelArgs* a, int nblk, int sm_count, int teams, int pw_bytes, unsigned long long sig, cudaStream_t st);
+int zpq_dec8_static_smem(void);
+int zpq_dec8_xchg_bytes(void);
+cudaError_t zpq_launch_dec8(const ZKernelArgs* a, const uint32_t* d_group_first, const uint32_t* d_group_count, int ngroups,
+                            int nbk, int pw_bytes, int nwarps, int sm_count, cudaStream_t st);
 cudaError_t zpq_launch_sha1(const uint8_t* const* ptr, const uint64_t* len, uint8_t* out, int n, cudaStream_t st);
 cudaError_t zpq_launch_gaps(const uint8_t* const* ptr, const uint64_t* len, int32_t* gaps, int n, int sm_count, cudaStream_t st);
 cudaError_t zpq_launch_scatter(const uint8_t* pool, const uint64_t* src_off, uint8_t* const* dst, const uint32_t* nbytes, int n, cudaStream_t st);

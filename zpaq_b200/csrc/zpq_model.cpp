@@ -503,6 +503,51 @@ int compile_model(const uint8_t* hdr, int hlen, ZModel* M, std::vector<uint8_t>*
     for (uint32_t s = 0; s < M->fast.nsteps && ok; ++s) if (((M->fast.sd[s] & 7u) == ZK_ISSE) != (s < nlev)) ok = false;
     M->fast.pair_ok = ok ? 1 : 0; M->fast.nlev = nlev;
   }
+  // lock-step decoder plan: needs the two-warp preconditions (flattened recipes, ISSE fed by ICM / ISSE), every MIX
+  // before every scalar step, and the role counts the kernel is built for
+  {
+    ZTPlan& T = M->tplan;
+    memset(&T, 0, sizeof(T));
+    bool ok = M->fast.pair_ok != 0 && M->wave.ok != 0;
+    bool seen_scalar = false;
+    for (int i = 0; i < n && ok; ++i) {
+      const ZComp& c = M->comp[i];
+      switch (c.type) {
+        case ZT_ICM: case ZT_ISSE:
+          if (T.nh >= ZPQ_T_HASH) { ok = false; break; }
+          T.hcomp[T.nh++] = (uint8_t)i;
+          if (c.type == ZT_ISSE) {
+            // the chain warp keeps one running value: an ISSE's input must be an ICM or the ISSE right before it
+            if (M->comp[c.a2].type == ZT_ISSE && !(T.nisse > 0 && T.icomp[T.nisse - 1] == c.a2)) ok = false;
+            if (T.nisse >= 16) ok = false;
+            T.isse_ord[i] = (uint8_t)T.nisse; T.icomp[T.nisse] = (uint8_t)i; T.ijn[T.nisse] = c.a2; ++T.nisse;
+          }
+          break;
+        case ZT_CM: case ZT_MATCH: case ZT_CONS:
+          if (T.nmisc >= ZPQ_T_MISC) { ok = false; break; }
+          T.mcomp[T.nmisc++] = (uint8_t)i;
+          break;
+        case ZT_MIX:
+          if (seen_scalar || c.a3 > 32) ok = false;        // a mixer fed by a scalar step; more inputs than a component warp has lanes for
+          break;
+        case ZT_MIX2: case ZT_SSE: case ZT_AVG:
+          if (T.nscalar >= ZPQ_T_SCALAR) { ok = false; break; }
+          T.scomp[T.nscalar++] = (uint8_t)i;
+          seen_scalar = true;
+          break;
+        default: ok = false;
+      }
+    }
+    // a mixer's inputs must be complete when the mix warp runs: components of warp A kinds, ISSE outputs, earlier mixers
+    for (int i = 0; i < n && ok; ++i)
+      if (M->comp[i].type == ZT_MIX)
+        for (int j = M->comp[i].a2; j < M->comp[i].a2 + M->comp[i].a3; ++j) {
+          const uint32_t t = M->comp[j].type;
+          if (t == ZT_MIX2 || t == ZT_SSE || t == ZT_AVG) ok = false;
+        }
+    if (T.nh == 0 || T.nh > 20) ok = false;                 // nh + 4 warps, 768 threads at most
+    T.ok = ok ? 1 : 0;
+  }
   return ZPQ_OK;
 }
 
