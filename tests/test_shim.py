@@ -126,3 +126,32 @@ def test_stream_api_through_the_gpu_library(tmp_path):
     assert rc == 0, out
     assert "-> GPU batch, status 0" in out, out
     assert (tmp_path / "out").read_bytes() == data
+
+
+@pytest.mark.skipif(not os.path.exists(STREAM), reason="stream driver not built (make -C oracle cli)")
+@pytest.mark.gpu
+def test_decompresser_handles_long_zero_runs_before_the_trailer(tmp_path):
+    """Decompresser::decompress / readSegmentEnd through the shim on every golden archive of the context-model family,
+    in pieces of 1000 bytes.  Eleven of them end their coded data with five to seven zero bytes (the last bytes of the
+    range flush are zero): the terminator is the LAST four zeros before the 253 / 254 marker (Decoder::skip,
+    libzpaq.cpp:2165), and the stored SHA-1 must still be found behind it."""
+    import base64
+    from util import load, data_of, archive_bytes
+    long_runs = 0
+    for e in load("archives.json"):
+        arc = archive_bytes(e)
+        if arc is None or len(arc) > 200000:
+            continue
+        blocks = O.parse_blocks(arc)
+        if not all(0 < b.header[6] for b in blocks):
+            continue
+        tail = arc[:-1]
+        tail = tail[:-21] if tail[-21] == 253 else tail[:-1]
+        long_runs += len(tail) - len(tail.rstrip(b"\0")) >= 5
+        (tmp_path / "a.zpaq").write_bytes(arc)
+        rc, out = _run(STREAM, ["D", "1000", "a.zpaq", "out"], tmp_path, log=True)
+        assert rc == 0, (e["name"], out)
+        assert "-> GPU" in out, out
+        want = data_of(e["data"]) if isinstance(e["data"], dict) else b"".join(data_of(d) for d in e["data"])
+        assert (tmp_path / "out").read_bytes() == want, e["name"]
+    assert long_runs >= 5

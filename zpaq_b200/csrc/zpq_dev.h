@@ -157,7 +157,7 @@ struct ZHashPlan {
   alignas(8) ZHashSlot slot[ZPQ_HSLOTS];
   uint32_t w[ZPQ_HSLOTS][32];            // operand word per lane (the flat op word; ZH_SEG: segment index in bits 8-9)
   uint32_t w2[ZPQ_HSLOTS][32];           // ZH_WORD: second word (multiplier, first flag)
-  // the two-warp decoders split the components over two warps (role 0: ICM ISSE CM CONST MATCH, role 1: the rest): the
+  // the two-warp decoders split the components over two warps (role 0: ICM ISSE MATCH, role 1: the rest): the
   // slots that touch a lane of each role, so that a warp walks only its own slots (zpq_kernels7.cu)
   uint8_t role_n[2];
   uint8_t role_slots[2][ZPQ_HSLOTS];

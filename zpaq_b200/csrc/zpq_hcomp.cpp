@@ -554,7 +554,7 @@ void build_hash_plan(ZModel* M) {
     uint32_t role_mask[2] = {0, 0};
     for (int l = 0; l < n; ++l) {
       const uint32_t t = M->comp[l].type;
-      const int role = (t == ZT_ICM || t == ZT_ISSE || t == ZT_CM || t == ZT_CONS || t == ZT_MATCH) ? 0 : 1;
+      const int role = (t == ZT_ICM || t == ZT_ISSE || t == ZT_MATCH) ? 0 : 1;        // the split zpq_kernels7.cu uses
       role_mask[role] |= 1u << l;
     }
     for (int r = 0; r < 2; ++r) {

@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
     u32* gtab = nullptr; u8* ht = nullptr;
     if (lane < n) {
       const ZComp cd = ZM->comp[lane];
-      const bool inA = cd.type == ZT_ICM || cd.type == ZT_ISSE || cd.type == ZT_CM || cd.type == ZT_CONS || cd.type == ZT_MATCH;
+      // warp A: the hash components and MATCH; warp B: everything else (CM / CONST moved to B in round 2: A was the longer stream)
+      const bool inA = cd.type == ZT_ICM || cd.type == ZT_ISSE || cd.type == ZT_MATCH;
       if ((role == 0) == inA) {
         type = cd.type; a1 = cd.a1; a2 = cd.a2; a3 = cd.a3; a4 = cd.a4; a5 = cd.a5;
         cm_mask = cd.cm_mask; ht_mask = cd.ht_mask; limit = cd.limit; level = ZM->fast.level[lane];
@@ -466,6 +467,10 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
       bool candv = false; int ylast = 0;
       const bool cand_ok = __all_sync(FULL, (type != ZT_MIX || ((a5 & 255u) == 255u && cm_mask >= 255u)) &&
                                             (type != ZT_SSE || cm_mask >= 256u * 32u - 1u));
+      // CM / CONST lanes of this warp: plain predict-after-update (warp B has the slack after it has sent the bit)
+      int p_ownB = (type == ZT_CONS) ? ((int)a1 - 128) * 4 : 0;
+      u32 cxaB = 0, cmv = 0;
+      if (type == ZT_CM) { cxaB = (h ^ 1u) & cm_mask; cmv = gtab[cxaB]; p_ownB = t_stretch(S, cmv >> 17); }
       int status = ST_OK;
       Dec7 C;
       C.low = 1; C.high = 0xffffffffu; C.curr = 0; C.status = ST_OK;
@@ -549,6 +554,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
             // ---- predictions of warp A's components ----
             BAR_SYNC64(barP);
             int pv = (int)pp[lane];                              // pv = prediction of component `lane` (warp A's lanes for now)
+            if (type == ZT_CM || type == ZT_CONS) pv = p_ownB;
             int pu[ZPQ_FAST_STEPS];                              // outputs of the steps, warp-uniform
             int xjs[ZPQ_FAST_STEPS], xks[ZPQ_FAST_STEPS];        // inputs of MIX2 steps (training), warp-uniform
             u32 ssek0 = 0, ssek1 = 0, ssev0 = 0, ssev1 = 0;     // SSE: bucket index / value to train, per SSE
@@ -637,6 +643,11 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
                 const int x = q == 0 ? mixx0 : (q == 1 ? mixx1 : mixx2);
                 if (lane < (int)mix_m[q]) mix_tab[q][mixbase[q] + lane] = clamp512k(w + ((err * x + (1 << 12)) >> 13));
               }
+            if (type == ZT_CM) {                                  // train(), libzpaq.h:1151-1157
+              const u32 count = cmv & 0x3ffu;
+              const int err = y * 32767 - (int)(cmv >> 17);
+              gtab[cxaB] = cmv + (((u32)err * (u32)__ldg(gdt + count)) & 0xfffffc00u) + (count < limit ? 1u : 0u);
+            }
             const int c8n = c8 * 2 + y;
             if (c8n >= 256) { cbyte = c8n - 256; BYTE_END7(cbyte); }
             else {
@@ -644,6 +655,7 @@ __global__ void __launch_bounds__(448, 1) zpq_dec_kernel7(const ZKernelArgs A, c
               if (c8n >= 16 && c8n < 32) hmap4 = (hmap4 & 0xf) << 5 | y << 4 | 1;
               else hmap4 = (hmap4 & 0x1f0) | (((hmap4 & 0xf) * 2 + y) & 0xf);
             }
+            if (type == ZT_CM) { cxaB = (h ^ (u32)hmap4) & cm_mask; cmv = gtab[cxaB]; p_ownB = t_stretch(S, cmv >> 17); }
           }
           if (failed) break;
           if (C.out_pos < C.out_cap) { if (lane == 0) C.out[C.out_pos] = (u8)cbyte; }
