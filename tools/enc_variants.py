@@ -4,6 +4,8 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oraclepy as O, zpaq_b200 as Z
+if os.environ.get("ZPQ_AB_LIB"):          # A/B against a library built from another commit (tools only; the package has no switch)
+    Z.LIB_PATH = os.path.abspath(os.environ["ZPQ_AB_LIB"]); print("library:", Z.LIB_PATH, flush=True)
 
 nblk = int(sys.argv[1]) if len(sys.argv) > 1 else 1029
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
