@@ -124,6 +124,9 @@ int zpq_decode_blocks_dev(zpq_ctx* ctx, int nblk, zpq_job* jobs);
 /* Device time (ms, CUDA events on the context's stream) of the last batch:
  * [0] arena initialisation kernel, [1] coding kernel, [2] whole call. */
 int zpq_last_timing(const zpq_ctx* ctx, float ms[3]);
+/* Device time (ms) of the stages in front of the coder in the last zpq_compress_blocks[_dev] call (both are part of
+ * zpq_last_timing's [0]): [0] SHA-1 + level-5 statistics, [1] E8E9 / BWT pre-processing. */
+int zpq_last_prep_timing(const zpq_ctx* ctx, float ms[2]);
 /* Number of kernel launches issued by this context so far. */
 uint64_t zpq_launch_count(const zpq_ctx* ctx);
 /* Diagnostics: blocks of the last batch coded by each kernel tier: [0] wavefront encoder (zpq_kernels5.cu),
@@ -155,6 +158,13 @@ int zpq_compress_blocks_dev(zpq_ctx* ctx, int nblk, const char* method,
                             int32_t* status);
 /* zpq_model_from_method with the payload statistics already taken (zpq_analyze_dev): gaps[2] as returned there. */
 int zpq_header_from_stats(const char* method, uint64_t n, const int32_t gaps[2], uint8_t* hdr, int cap, int* hlen);
+/* What zpq_compress_blocks does with a method, for callers that want to see or reuse the plan: the header bytes, the
+ * pre-processing of the payload (makeConfig's second number, libzpaq.cpp:6894: 0 none, 3 BWT, 4 E8E9, 7 E8E9 then BWT --
+ * LZBuffer level 3 and e8e9(), libzpaq.cpp:6450-6459, 6649-6658) and the bytes that pass through the model in front of
+ * the (transformed) payload: "0" (PASS) or "1, len, PCOMP program" (Compressor::postProcess, libzpaq.cpp:2888-2915).
+ * LZ77 methods return ZPQ_E_METHOD. */
+int zpq_block_plan(const char* method, uint64_t n, const int32_t gaps[2], uint8_t* hdr, int hdr_cap, int* hlen,
+                   int* prep, uint8_t* prefix, int prefix_cap, int* prefix_len);
 /* Device-side analysis of payloads in HBM: sha1 = 20 bytes per block (or NULL), gaps = 2 ints per block (the dominant
  * byte-gap periods level 5 models, 0 = none; or NULL).  Results are host arrays. */
 int zpq_analyze_dev(zpq_ctx* ctx, int nblk, const uint8_t* const* d_data, const uint64_t* len,

@@ -100,6 +100,12 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
   for (int l = 0; l < 32; ++l) if (((tp >> l) & 1u) && a[l]) r |= 1u << l;
   return r;
 }
+static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+  unsigned tp; const uint64_t* a = simt_warp_exchange(mask, v, &tp);
+  unsigned r = 0;
+  for (int l = 0; l < 32; ++l) if (((tp >> l) & 1u) && (unsigned)a[l] == v) r |= 1u << l;
+  return r;
+}
 static inline int __all_sync(unsigned mask, int pred) {
   unsigned tp; const uint64_t* a = simt_warp_exchange(mask, pred ? 1u : 0u, &tp);
   for (int l = 0; l < 32; ++l) if (((tp >> l) & 1u) && !a[l]) return 0;

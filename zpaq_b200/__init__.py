@@ -62,7 +62,7 @@ EXPORTS = ["zpq_abi_version", "zpq_create", "zpq_destroy", "zpq_strerror", "zpq_
            "zpq_encode_blocks", "zpq_decode_blocks", "zpq_encode_blocks_dev", "zpq_decode_blocks_dev",
            "zpq_last_timing", "zpq_launch_count", "zpq_compress_blocks", "zpq_decompress_archive",
            "zpq_compress_bound", "zpq_postprocess_block", "zpq_model_describe", "zpq_last_tiers",
-           "zpq_compress_blocks_dev", "zpq_analyze_dev", "zpq_scan_archive", "zpq_header_from_stats"]
+           "zpq_compress_blocks_dev", "zpq_analyze_dev", "zpq_scan_archive", "zpq_header_from_stats", "zpq_block_plan", "zpq_last_prep_timing"]
 
 _lib = None
 
@@ -91,6 +91,7 @@ def lib():
         for f in (L.zpq_encode_blocks, L.zpq_decode_blocks, L.zpq_encode_blocks_dev, L.zpq_decode_blocks_dev):
             f.argtypes = [vp, i32, C.POINTER(Job)]
         L.zpq_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
+        L.zpq_last_prep_timing.argtypes = [vp, C.POINTER(C.c_float)]
         L.zpq_launch_count.argtypes = [vp]
         L.zpq_last_tiers.argtypes = [vp, C.POINTER(C.c_uint32)]
         L.zpq_launch_count.restype = u64
@@ -99,6 +100,7 @@ def lib():
         L.zpq_analyze_dev.argtypes = [vp, i32, vp, vp, vp, vp]
         L.zpq_scan_archive.argtypes = [vp, u64, vp, i32, C.POINTER(i32), C.POINTER(i32)]
         L.zpq_decompress_archive.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(i32), i32]
+        L.zpq_block_plan.argtypes = [C.c_char_p, u64, vp, C.c_char_p, i32, C.POINTER(i32), C.POINTER(i32), C.c_char_p, i32, C.POINTER(i32)]
         L.zpq_compress_bound.argtypes = [u64]
         L.zpq_postprocess_block.argtypes = [C.c_char_p, i32, vp, vp, i32, vp, u64, C.POINTER(u64), vp]
         L.zpq_compress_bound.restype = u64
@@ -117,6 +119,19 @@ def model_from_method(method, data=b""):
     if rc:
         raise ZpqError(rc)
     return out.raw[:n.value]
+
+
+def block_plan(method, n, gaps=(0, 0)):
+    """(header bytes, pre-processing kind 0 / 3 / 4 / 7, bytes that go through the model in front of the payload) of a
+    method for a block of n bytes -- what zpq_compress_blocks builds per block."""
+    hdr = C.create_string_buffer(70000)
+    pre = C.create_string_buffer(70000)
+    hl, pl, prep = C.c_int(0), C.c_int(0), C.c_int(0)
+    g = (C.c_int32 * 2)(*gaps)
+    rc = lib().zpq_block_plan(method.encode(), n, g, hdr, 70000, C.byref(hl), C.byref(prep), pre, 70000, C.byref(pl))
+    if rc:
+        raise ZpqError(rc)
+    return hdr.raw[:hl.value], prep.value, pre.raw[:pl.value]
 
 
 def postprocess_block(hdr, model_out_segments):

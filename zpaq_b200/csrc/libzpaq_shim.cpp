@@ -56,7 +56,9 @@ struct Req {
 
 // how long the submitter waits for more blocks before it launches (zpaq keeps at most `-threads` blocks in flight, and a
 // launch is bound by the latency of one block, so waiting a few milliseconds for all of them costs nothing): ZPQ_SHIM_WINDOW_MS
-int window_ms() { static const int ms = [] { const char* e = getenv("ZPQ_SHIM_WINDOW_MS"); const int v = e ? atoi(e) : 2; return v < 0 ? 0 : (v > 1000 ? 1000 : v); }(); return ms; }
+int window_ms() { static const int ms = [] { const char* e = getenv("ZPQ_SHIM_WINDOW_MS"); const int v = e ? atoi(e) : 100; return v < 0 ? 0 : (v > 1000 ? 1000 : v); }(); return ms; }
+
+int max_wait_ms() { static const int ms = [] { const char* e = getenv("ZPQ_SHIM_MAX_WAIT_MS"); const int v = e ? atoi(e) : 3000; return v < 0 ? 0 : (v > 10000 ? 10000 : v); }(); return ms; }
 
 struct Batcher {
   std::mutex mu; std::condition_variable cv_submit, cv_done;
@@ -70,11 +72,23 @@ struct Batcher {
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_submit.wait(lk, [&] { return !queue.empty(); });
-        // give concurrently running compress threads a moment to add their blocks (zpaq keeps
-        // `threads` blocks in flight), then take everything that is queued
-        lk.unlock();
-        std::this_thread::sleep_for(std::chrono::milliseconds(window_ms()));
-        lk.lock();
+        // give concurrently running compress / decompress threads time to add their blocks (zpaq keeps `-threads`
+        // blocks in flight: `zpaq add -threads 512` hands over 1 023 blocks as fast as the reader thread fills them).
+        // A launch is bound by the latency of ONE block (about ten seconds for a 1 MiB block at level 5, whatever the
+        // batch size), so a batch should be everything the caller will supply: keep waiting in steps of
+        // ZPQ_SHIM_WINDOW_MS (100 ms: zpaq's reader thread fragments and hashes at ~100 MB/s, a block every ~10 ms) while
+        // the queue is still growing, at most ZPQ_SHIM_MAX_WAIT_MS (3 s) in all.  Measured: profiles/r02q_cli_threads.log
+        const auto t0 = std::chrono::steady_clock::now();
+        size_t seen = queue.size();
+        for (;;) {
+          lk.unlock();
+          std::this_thread::sleep_for(std::chrono::milliseconds(window_ms()));
+          lk.lock();
+          const bool grew = queue.size() != seen;
+          seen = queue.size();
+          const auto waited = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+          if (!grew || waited >= max_wait_ms()) break;
+        }
         batch.swap(queue);
       }
       if (ctx_rc == 1) ctx_rc = zpq_create(0, &ctx);

@@ -66,6 +66,8 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   float ms_prep = 0;           // device time of the last analysis pass (SHA-1, gap statistics); added to ms[0] by the whole-block calls
+  float ms_xform = 0;          // device time of the last pre-processing pass (E8E9, BWT: zpq_bwt.cu); added to ms[0] as well
+  DevBuf d_xform, d_xws;       // transformed payloads; workspace of the suffix sorter
   uint64_t launches = 0;
   uint32_t tiers[7] = {0, 0, 0, 0, 0, 0, 0};   // blocks of the last batch per kernel tier (zpq_last_tiers)
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
@@ -587,7 +589,7 @@ void zpq_destroy(zpq_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release(); ctx->d_prep.release(); ctx->d_stage_in.release(); ctx->d_stage_out.release(); for (int i = 0; i < 4; ++i) ctx->d_groups[i].release();
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release(); ctx->d_prep.release(); ctx->d_xform.release(); ctx->d_xws.release(); ctx->d_stage_in.release(); ctx->d_stage_out.release(); for (int i = 0; i < 4; ++i) ctx->d_groups[i].release();
   if (ctx->own_ws && ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -663,6 +665,34 @@ int zpq_header_from_stats(const char* method, uint64_t n, const int32_t gaps[2],
   return ZPQ_OK;
 }
 
+// header + pre-processing kind + model prefix of a method (what compress_core builds per block)
+static int plan_block(const char* method, uint64_t n, const int g[2], std::vector<uint8_t>* hdr, int* prep, std::vector<uint8_t>* prefix, std::string* err) {
+  int size_class = 0;
+  const int rc = block_plan(method, n, g, hdr, prep, &size_class, err);
+  if (rc != ZPQ_OK) return rc;
+  prefix->assign(1, 0);                                  // PASS
+  if (*prep != 0) {
+    std::vector<uint8_t> code;
+    const int rp = pcomp_program(*prep, size_class, &code);
+    if (rp != ZPQ_OK) { *err = "no post-processor program for this pre-processing"; return rp; }
+    pcomp_prefix(code, prefix);
+  }
+  return ZPQ_OK;
+}
+
+int zpq_block_plan(const char* method, uint64_t n, const int32_t gaps[2], uint8_t* hdr, int hdr_cap, int* hlen,
+                   int* prep, uint8_t* prefix, int prefix_cap, int* prefix_len) {
+  if (!method || !hdr || !hlen || !prep || !prefix || !prefix_len) return ZPQ_E_ARG;
+  std::vector<uint8_t> h, pre; std::string e;
+  const int g[2] = {gaps ? gaps[0] : 0, gaps ? gaps[1] : 0};
+  const int rc = plan_block(method, n, g, &h, prep, &pre, &e);
+  if (rc != ZPQ_OK) return rc;
+  if ((int)h.size() > hdr_cap || (int)pre.size() > prefix_cap) return ZPQ_E_OUTPUT_FULL;
+  memcpy(hdr, h.data(), h.size()); *hlen = (int)h.size();
+  memcpy(prefix, pre.data(), pre.size()); *prefix_len = (int)pre.size();
+  return ZPQ_OK;
+}
+
 int zpq_encode_blocks(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, false, false); }
 int zpq_decode_blocks(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, true, false); }
 int zpq_encode_blocks_dev(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_batch(ctx, nblk, jobs, false, true); }
@@ -671,6 +701,12 @@ int zpq_decode_blocks_dev(zpq_ctx* ctx, int nblk, zpq_job* jobs) { return abi_ba
 int zpq_last_timing(const zpq_ctx* ctx, float ms[3]) {
   if (!ctx || !ms) return ZPQ_E_ARG;
   ms[0] = ctx->ms[0]; ms[1] = ctx->ms[1]; ms[2] = ctx->ms[2];
+  return ZPQ_OK;
+}
+
+int zpq_last_prep_timing(const zpq_ctx* ctx, float ms[2]) {
+  if (!ctx || !ms) return ZPQ_E_ARG;
+  ms[0] = ctx->ms_prep; ms[1] = ctx->ms_xform;
   return ZPQ_OK;
 }
 
@@ -743,7 +779,6 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
   CK(cudaSetDevice(ctx->device), "cudaSetDevice");
   cudaStream_t stream = ctx->stream;
   const auto t_begin = std::chrono::steady_clock::now();
-  static const uint8_t kPass = 0;   // post-processor flag PASS goes through the model first (libzpaq.cpp:2914)
   std::vector<int> st(nblk, ZPQ_OK);
   for (int i = 0; i < nblk; ++i) if (len[i] > 0x7fffffffull - 4096) st[i] = ZPQ_E_ARG;
 
@@ -773,14 +808,15 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
     const int rc = analyze_dev(ctx, nblk, aptr.data(), alen.data(), dosha1 ? sha.data() : nullptr, need_gaps ? gaps.data() : nullptr);
     if (rc != ZPQ_OK) return rc;
   }
-  // ---- host: header bytes and block prologue from (method, length, gaps) ----
-  std::vector<std::vector<uint8_t>> hdrs(nblk), pro(nblk);
+  // ---- host: header bytes, pre-processing kind, model prefix and block prologue from (method, length, gaps) ----
+  std::vector<std::vector<uint8_t>> hdrs(nblk), pro(nblk), prefix(nblk);
+  std::vector<int> prep(nblk, 0);
   for (int i = 0; i < nblk; ++i) {
     if (st[i] != ZPQ_OK) continue;
     std::string e;
     const int g2[2] = {gaps[2 * i], gaps[2 * i + 1]};
-    st[i] = header_from_stats(method, len[i], g2, &hdrs[i], &e);
-    if (st[i] != ZPQ_OK) continue;
+    st[i] = plan_block(method, len[i], g2, &hdrs[i], &prep[i], &prefix[i], &e);
+    if (st[i] != ZPQ_OK) { if (ctx->err.empty() || st[i] == ZPQ_E_METHOD) ctx->err = e; continue; }
     char cs[32];
     snprintf(cs, sizeof(cs), "%llu", (unsigned long long)len[i]);
     std::string comment = cs;                                   // libzpaq.cpp:7702-7703
@@ -788,6 +824,72 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
     write_block_prologue(&pro[i], hdrs[i].data(), (int)hdrs[i].size(), filenames ? filenames[i] : nullptr, comment.c_str());
     const uint64_t tail = 4 + (dosha1 ? 21 : 1) + 1;
     if (out_cap[i] < pro[i].size() + tail + 8) st[i] = ZPQ_E_OUTPUT_FULL;
+  }
+  // ---- pre-processing on the device (LZBuffer level 3 and e8e9(), libzpaq.cpp:6450-6459, 6630-6658): zpq_bwt.cu ----
+  std::vector<const uint8_t*> d_model_in(d_data);                // what goes through the model after the prefix
+  std::vector<uint64_t> model_len(len, len + nblk);
+  ctx->ms_xform = 0;
+  {
+    uint64_t tot = 0;
+    std::vector<uint64_t> off_e8(nblk, 0), off_bwt(nblk, 0);
+    bool any = false;
+    for (int i = 0; i < nblk; ++i) {
+      if (st[i] != ZPQ_OK || prep[i] == 0) continue;
+      any = true;
+      if (prep[i] & 4) { off_e8[i] = tot; tot = align_up(tot + len[i] + 16, 256); }
+      if ((prep[i] & 3) == 3) { off_bwt[i] = tot; tot = align_up(tot + len[i] + 5 + 16, 256); }
+    }
+    if (any) {
+      CK(ctx->d_xform.reserve(tot + 256), "pre-processing cudaMalloc");
+      uint8_t* dx = (uint8_t*)ctx->d_xform.p;
+      CK(cudaEventRecord(ctx->ev[0], stream), "event");
+      // E8E9 into a working copy
+      {
+        std::vector<const uint8_t*> ein; std::vector<uint8_t*> eout; std::vector<uint64_t> elen;
+        for (int i = 0; i < nblk; ++i) {
+          if (st[i] != ZPQ_OK || !(prep[i] & 4)) continue;
+          if (len[i]) CK(cudaMemcpyAsync(dx + off_e8[i], d_data[i], len[i], cudaMemcpyDeviceToDevice, stream), "E8E9 working copy");
+          ein.push_back(d_data[i]); eout.push_back(dx + off_e8[i]); elen.push_back(len[i]);
+          d_model_in[i] = dx + off_e8[i];
+        }
+        for (size_t k = 0; k < ein.size(); k += 60000) {
+          const int cnt = (int)std::min<size_t>(60000, ein.size() - k);
+          CK(ctx->d_xws.reserve((uint64_t)cnt * 24 + 1024), "pre-processing cudaMalloc");
+          CK(zpq_e8e9_forward(ein.data() + k, eout.data() + k, elen.data() + k, cnt, ctx->d_xws.p, ctx->sm_count, stream, &ctx->launches), "zpq_e8e9_kernel launch");
+        }
+      }
+      // BWT in sub-batches of at most 256 MiB (the sorter keeps ~51 bytes of state per payload byte)
+      {
+        std::vector<int> ids;
+        for (int i = 0; i < nblk; ++i) if (st[i] == ZPQ_OK && (prep[i] & 3) == 3) ids.push_back(i);
+        size_t k = 0;
+        while (k < ids.size()) {
+          uint64_t sum = 0; size_t e = k;
+          while (e < ids.size() && e - k < 60000 && (e == k || sum + len[ids[e]] <= ((uint64_t)1 << 28))) sum += len[ids[e++]];
+          std::vector<const uint8_t*> bin; std::vector<uint8_t*> bout; std::vector<uint64_t> blen;
+          for (size_t j = k; j < e; ++j) {
+            const int i = ids[j];
+            bin.push_back(d_model_in[i]); bout.push_back(dx + off_bwt[i]); blen.push_back(len[i]);
+          }
+          const uint64_t need = zpq_bwt_workspace(sum, (int)(e - k));
+          if (ctx->d_xws.reserve(need) != cudaSuccess) {
+            cudaGetLastError();
+            for (size_t j = k; j < e; ++j) st[ids[j]] = ZPQ_E_NOMEM;
+            ctx->err = "Out of memory";
+          }
+          else {
+            CK(zpq_bwt_forward(bin.data(), blen.data(), bout.data(), (int)(e - k), ctx->d_xws.p, ctx->d_xws.cap, ctx->sm_count, stream, &ctx->launches), "BWT kernels");
+            for (size_t j = k; j < e; ++j) { const int i = ids[j]; d_model_in[i] = dx + off_bwt[i]; model_len[i] = len[i] + 5; }
+          }
+          k = e;
+        }
+      }
+      CK(cudaEventRecord(ctx->ev[1], stream), "event");
+      CK(cudaStreamSynchronize(stream), "pre-processing");
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+      ctx->ms_xform = ms;
+    }
   }
   // ---- output blocks in HBM ----
   std::vector<uint8_t*> d_out(nblk, nullptr);
@@ -807,15 +909,15 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
     const uint64_t tail = 4 + (dosha1 ? 21 : 1) + 1;
     IJob J;
     J.hdr = hdrs[i].data(); J.hlen = (int)hdrs[i].size();
-    J.in.push_back(Piece{&kPass, 1});
-    J.in.push_back(Piece{d_data[i], len[i]});
-    J.seg_len.assign(1, len[i] + 1);
+    J.in.push_back(Piece{prefix[i].data(), prefix[i].size()});      // PASS byte, or "1, len, PCOMP program" (libzpaq.cpp:2905-2915)
+    J.in.push_back(Piece{d_model_in[i], model_len[i]});
+    J.seg_len.assign(1, model_len[i] + prefix[i].size());
     J.out = d_out[i] + pro[i].size();
     J.out_cap = out_cap[i] - pro[i].size() - tail;
     jobs.push_back(J); idx.push_back(i);
   }
   int rc = run_batch(ctx, jobs, false, false);
-  const float ms_init = ctx->ms[0] + ctx->ms_prep, ms_code = ctx->ms[1];
+  const float ms_init = ctx->ms[0] + ctx->ms_prep + ctx->ms_xform, ms_code = ctx->ms[1];
   // ---- framing around the coded data (Compressor::endSegment / endBlock, libzpaq.cpp:2956-3002), written on the device ----
   {
     std::vector<uint8_t> pool; std::vector<uint64_t> src_off; std::vector<uint8_t*> dst; std::vector<uint32_t> nb;

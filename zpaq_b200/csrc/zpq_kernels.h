@@ -31,6 +31,12 @@ cudaError_t zpq_launch_sha1(const uint8_t* const* ptr, const uint64_t* len, uint
 cudaError_t zpq_launch_gaps(const uint8_t* const* ptr, const uint64_t* len, int32_t* gaps, int n, int sm_count, cudaStream_t st);
 cudaError_t zpq_launch_scatter(const uint8_t* pool, const uint64_t* src_off, uint8_t* const* dst, const uint32_t* nbytes, int n, cudaStream_t st);
 cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant);
+// zpq_bwt.cu: forward transforms in front of the model; in / out are HOST arrays of DEVICE pointers, len is host memory
+uint64_t zpq_bwt_workspace(uint64_t total, int nb);
+cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, int nb,
+                            void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches);
+cudaError_t zpq_e8e9_forward(const uint8_t* const* in, uint8_t* const* out, const uint64_t* len, int nb, void* ws,
+                             int sm_count, cudaStream_t st, uint64_t* launches);
 unsigned long long zpq_code2_signature(const ZFast* F);
 cudaError_t zpq_launch_code2(const ZKernelArgs* a, int nblk, int decode, int sm_count, int warps, int pw_bytes,
                              unsigned long long sig, cudaStream_t st);

@@ -86,8 +86,9 @@ std::vector<int> dominant_gaps(const uint8_t* p, unsigned n) {
 }
 
 // "LB[,R,T]": L = level digit, B = block size digits (ignored here: the block decides), R,T -> block type R*4+T
-// (bit 0 text, bit 1 exe; 512 when no type is given).  Only the context-mixing branches of levels 4 and 5 are in scope.
-int level_tokens(const std::string& m, uint64_t n64, const std::vector<int>& gaps, int* arg0, std::vector<Token>* out, std::string* err) {
+// (bit 0 text, bit 1 exe; 512 when no type is given).  In scope: the context-mixing branches of levels 4 and 5 and the
+// BWT branches of levels 3 and 4, each with or without E8E9 (*prep = makeConfig's pre-processing number: 0, 3, 4, 7).
+int level_tokens(const std::string& m, uint64_t n64, const std::vector<int>& gaps, int* arg0, int* prep, std::vector<Token>* out, std::string* err) {
   const unsigned n = (unsigned)n64;
   *arg0 = std::max(bit_length(n + 4095) - 20, 0);
   int field[4] = {0, 0, 0, 0}, nsep = 0;
@@ -98,14 +99,26 @@ int level_tokens(const std::string& m, uint64_t n64, const std::vector<int>& gap
   const unsigned type = nsep == 0 ? 512u : (unsigned)(field[1] * 4 + field[2]);
   const bool text = (type & 1u) != 0, exe = (type & 2u) != 0;
   const int level = m[0] - '0';
-  if (level <= 3) { *err = "levels 0-3 use LZ77/BWT pre-processing, which is outside the context-mixing path"; return ZPQ_E_METHOD; }
-  if (level == 4 && (type < 48 || type >= 900)) {
-    *err = "level 4 selects store/LZ77/BWT for this block type: outside the context-mixing path"; return ZPQ_E_METHOD;
-  }
-  if (exe) { *err = "E8E9 pre-processing (exe block type) is outside the context-mixing path"; return ZPQ_E_METHOD; }
+  const int e8 = exe ? 4 : 0;                  // E8E9 address rewriting in front of whatever the level selects
   std::vector<Token>& t = *out;
   t.clear();
+  *prep = e8;
+  const char* kLz = "this block type selects store / LZ77 at this level: outside the context-mixing and BWT paths";
+  if (level <= 2) { *err = "levels 0-2 are store / LZ77 only: outside the context-mixing and BWT paths"; return ZPQ_E_METHOD; }
+  if (level == 3) {
+    // BWT for text and for highly redundant blocks; everything else at this level is LZ77
+    if (type < 48 || !(type >= 640 || text)) { *err = kLz; return ZPQ_E_METHOD; }
+    *prep = 3 + e8;
+    t.push_back(tok('c')); t.push_back(tok('i', {1}));
+    return ZPQ_OK;
+  }
   if (level == 4) {
+    if (type < 48) { *err = kLz; return ZPQ_E_METHOD; }
+    if (type >= 900) {
+      *prep = 3 + e8;
+      t.push_back(tok('c')); t.push_back(tok('i', {1}));
+      return ZPQ_OK;
+    }
     // order 0..5 chain, match model, optional word model, one mixer
     t.push_back(tok('c'));
     t.push_back(tok('i', {1, 1, 1, 1, 2}));
@@ -331,8 +344,8 @@ const Family kFamilies[] = {
 };
 
 // ---------------------------------------------------------------- 4. header bytes
-// hsize[2] hh hm ph pm n COMP 0 HCOMP 0   ("comp 9 16 0 0", libzpaq.cpp:7307)
-int serialise(const Draft& d, std::vector<uint8_t>* hdr, std::string* err) {
+// hsize[2] hh hm ph pm n COMP 0 HCOMP 0   ("comp 9 16 0 0", libzpaq.cpp:7307; BWT blocks: ph = pm = 20 + size class, 7137)
+int serialise(const Draft& d, int ph, int pm, std::vector<uint8_t>* hdr, std::string* err) {
   static const int kBytes[10] = {0, 2, 3, 2, 3, 4, 6, 6, 3, 5};
   std::vector<uint8_t> comp;
   for (const Record& r : d.comps) {
@@ -342,7 +355,7 @@ int serialise(const Draft& d, std::vector<uint8_t>* hdr, std::string* err) {
   const size_t hsize = 5 + comp.size() + 1 + d.code.size() + 1;
   if (hsize > 65535) { *err = "program too big"; return ZPQ_E_METHOD; }
   hdr->clear();
-  const uint8_t fixed[7] = {(uint8_t)(hsize & 255), (uint8_t)(hsize >> 8), 9, 16, 0, 0, (uint8_t)d.count()};
+  const uint8_t fixed[7] = {(uint8_t)(hsize & 255), (uint8_t)(hsize >> 8), 9, 16, (uint8_t)ph, (uint8_t)pm, (uint8_t)d.count()};
   hdr->insert(hdr->end(), fixed, fixed + 7);
   hdr->insert(hdr->end(), comp.begin(), comp.end());
   hdr->push_back(0);
@@ -370,7 +383,9 @@ int header_from_method(const char* method_, const uint8_t* data, uint64_t n, std
   return header_from_stats(method_, n, gaps, hdr, err);
 }
 
-int header_from_stats(const char* method_, uint64_t n, const int gaps_in[2], std::vector<uint8_t>* hdr, std::string* err) {
+// method (+ payload statistics) -> header bytes and the pre-processing the payload needs before it enters the model:
+// *prep = 0 none, 3 BWT, 4 E8E9, 7 E8E9 then BWT (makeConfig's second number, libzpaq.cpp:6894); LZ77 kinds are not built
+int block_plan(const char* method_, uint64_t n, const int gaps_in[2], std::vector<uint8_t>* hdr, int* prep, int* size_class_out, std::string* err) {
   std::string e0;
   if (!err) err = &e0;
   if (!method_ || !method_[0]) { *err = "empty method"; return ZPQ_E_METHOD; }
@@ -381,11 +396,11 @@ int header_from_stats(const char* method_, uint64_t n, const int gaps_in[2], std
   if (isdigit((unsigned char)ms[0])) {
     std::vector<int> gaps;
     for (int i = 0; i < 2 && gaps_in && gaps_in[i] > 0; ++i) gaps.push_back(gaps_in[i]);
-    const int rc = level_tokens(ms, n, gaps, &size_class, &tokens, err);
+    const int rc = level_tokens(ms, n, gaps, &size_class, &preprocessing, &tokens, err);
     if (rc != ZPQ_OK) return rc;
   }
   else if (ms[0] == 'x') {
-    // "x" N1 [, N2 ...]: block size class, pre-processing type (must be 0 here), further arguments of the pre-processor;
+    // "x" N1 [, N2 ...]: block size class, pre-processing type, further arguments of the pre-processor;
     // up to nine numbers, then the component tokens (libzpaq.cpp:6893-6913)
     const char* s = ms.c_str() + 1;
     int head[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k = 0;
@@ -397,8 +412,12 @@ int header_from_stats(const char* method_, uint64_t n, const int gaps_in[2], std
     tokens = tokenize(s);
   }
   else { *err = "Unsupported method"; return ZPQ_E_METHOD; }
-  if (preprocessing != 0) { *err = "pre-processing (LZ77/BWT/E8E9) is outside the context-mixing path"; return ZPQ_E_METHOD; }
+  if (preprocessing != 0 && preprocessing != 3 && preprocessing != 4 && preprocessing != 7) {
+    *err = "LZ77 pre-processing is outside the context-mixing and BWT paths"; return ZPQ_E_METHOD;
+  }
   if (size_class > 11) { *err = "block size argument too big"; return ZPQ_E_METHOD; }
+  // the inverse BWT keeps the block (n + 5 bytes) in a 2^(20 + size class) byte array
+  if ((preprocessing & 3) == 3 && n + 4096 > ((uint64_t)0x100000 << size_class)) { *err = "block does not fit the method's block size"; return ZPQ_E_METHOD; }
 
   Draft d;
   d.membits = size_class + 20;
@@ -409,7 +428,22 @@ int header_from_stats(const char* method_, uint64_t n, const int gaps_in[2], std
   }
   one(d, HALT);
   if (!d.ok || !d.open_jumps.empty() || d.count() > 255) { *err = "method arguments out of range"; return ZPQ_E_METHOD; }
-  return serialise(d, hdr, err);
+  const bool bwt = (preprocessing & 3) == 3;
+  if (prep) *prep = preprocessing;
+  if (size_class_out) *size_class_out = size_class;
+  return serialise(d, bwt ? size_class + 20 : 0, bwt ? size_class + 20 : 0, hdr, err);
+}
+
+// header only, for callers that feed the model themselves (zpq_model_from_method, zpq_header_from_stats): a method that
+// transforms the payload is refused here -- the header alone would describe a block the caller cannot produce
+int header_from_stats(const char* method_, uint64_t n, const int gaps_in[2], std::vector<uint8_t>* hdr, std::string* err) {
+  std::string e0;
+  if (!err) err = &e0;
+  int prep = 0;
+  const int rc = block_plan(method_, n, gaps_in, hdr, &prep, nullptr, err);
+  if (rc != ZPQ_OK) return rc;
+  if (prep != 0) { hdr->clear(); *err = "this method pre-processes the payload (E8E9 / BWT): use zpq_compress_blocks"; return ZPQ_E_METHOD; }
+  return ZPQ_OK;
 }
 
 }  // namespace zpq
