@@ -24,4 +24,27 @@ out, nb = ctx.decompress_archive(b"".join(blocks), 2700)
 assert nb == 2 and out == O.gen_block(1, 7, 1800) + O.gen_block(3, 8, 900)
 assert ctx.launch_count() > 0
 ctx.close()
-print("simt preflight ok: %d blocks" % checked)
+
+# pre-processing kernels (zpq_bwt.cu): BWT, E8E9 + BWT, E8E9 + CM against blocks written by the unmodified reference
+import hashlib
+import json
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from util import transform_payload
+gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "transforms.json")))["cases"]
+ctx = Z.Context(0)
+by_method = {}
+for c in gold:
+    if c["n"] <= 12000:
+        by_method.setdefault(c["method"], []).append(c)
+nt = 0
+for method, cs in by_method.items():
+    blocks = ctx.compress_blocks(method, [transform_payload(c) for c in cs])
+    for c, b in zip(cs, blocks):
+        assert len(b) == c["block_len"] and hashlib.sha1(b).hexdigest() == c["block_sha1"], ("transform", method, c["n"])
+        nt += 1
+    out, nb = ctx.decompress_archive(b"".join(blocks), sum(c["n"] for c in cs))
+    assert nb == len(cs) and out == b"".join(transform_payload(c) for c in cs), ("transform round trip", method)
+ctx.close()
+print("simt preflight ok: %d blocks, %d transformed blocks" % (checked, nt))

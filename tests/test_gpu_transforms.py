@@ -1,0 +1,77 @@
+"""GPU parity for the pre-processing kernels (zpq_bwt.cu): zpq_compress_blocks with a BWT / E8E9 method must write the
+bytes libzpaq::compressBlock writes (LZBuffer level 3 + e8e9 + makeConfig's PCOMP, libzpaq.cpp:6450-6658, 7135-7323)."""
+import hashlib
+
+import pytest
+
+import oraclepy as O
+import zpaq_b200 as Z
+from util import exe_like, load, transform_payload
+
+pytestmark = pytest.mark.gpu
+GOLD = load("transforms.json")["cases"]
+
+
+def _by_method():
+    d = {}
+    for c in GOLD:
+        d.setdefault(c["method"], []).append(c)
+    return sorted(d.items())
+
+
+@pytest.mark.parametrize("method,cases", _by_method(), ids=[m for m, _ in _by_method()])
+def test_blocks_equal_the_reference_goldens(ctx, method, cases):
+    pays = [transform_payload(c) for c in cases]
+    l0 = ctx.launch_count()
+    blocks = ctx.compress_blocks(method, pays)
+    assert ctx.launch_count() > l0
+    for c, b in zip(cases, blocks):
+        assert len(b) == c["block_len"] and hashlib.sha1(b).hexdigest() == c["block_sha1"], (method, c["n"])
+    out, nb = ctx.decompress_archive(b"".join(blocks), sum(len(p) for p in pays))
+    assert nb == len(pays) and out == b"".join(pays)
+
+
+def test_full_size_batch_against_the_live_reference(ctx):
+    """48 blocks x 1 044 480 B of three kinds through BWT in one call (one index space for all suffixes), two of them and one
+    E8E9 + BWT block compared with the unmodified reference, all of them decoded again."""
+    import refpy as R
+    n = (1 << 20) - 4096
+    pays = [O.gen_block(k % 3, 7000 + k, n) for k in range(48)]
+    blocks = ctx.compress_blocks("x0,3ci1", pays)
+    if R.available():
+        for k in (0, 1):
+            assert blocks[k] == R.compress_block(pays[k], "x0,3ci1"), k
+    out, nb = ctx.decompress_archive(b"".join(blocks[:6]), 6 * n)
+    assert nb == 6 and out == b"".join(pays[:6])
+    e = exe_like(99, n)
+    be = ctx.compress_blocks("x0,7ci1", [e])[0]
+    if R.available():
+        assert be == R.compress_block(e, "x0,7ci1")
+    out, nb = ctx.decompress_archive(be, n)
+    assert out == e
+
+
+def test_block_above_16_mib_uses_the_other_program(ctx):
+    """size class 5 (one block of 17 MiB): the post-processor is the list traversal without the packed cells, ph = pm = 25."""
+    import refpy as R
+    n = 17 << 20
+    p = O.gen_block(0, 4242, n)
+    b = ctx.compress_blocks("35,200,1", [p])[0]
+    hdr = O.parse_blocks(b)[0].header
+    assert hdr[4] == 25 and hdr[5] == 25
+    if R.available():
+        assert b == R.compress_block(p, "35,200,1")
+    out, nb = ctx.decompress_archive(b, n)
+    assert nb == 1 and out == p
+
+
+def test_degenerate_payloads(ctx):
+    """long runs and long repeats: many doubling rounds, groups that stay large"""
+    import refpy as R
+    pays = [b"\0" * 300000, b"abcd" * 60000, bytes(range(256)) * 500, b"a" * 70000 + b"b" + b"a" * 70000]
+    blocks = ctx.compress_blocks("x0,3ci1", pays)
+    if R.available():
+        for p, b in zip(pays, blocks):
+            assert b == R.compress_block(p, "x0,3ci1")
+    out, nb = ctx.decompress_archive(b"".join(blocks), sum(len(p) for p in pays))
+    assert out == b"".join(pays)

@@ -74,3 +74,21 @@ class DevBytes:
             torch.cuda.synchronize()
             return bytes(self.t[:n].cpu().numpy().tobytes())
         return self.buf.raw[:n]
+
+
+def exe_like(seed, n):
+    """Deterministic payload with x86-looking CALL / JMP patterns (E8 / E9 .. .. .. 00 / FF), including overlapping candidates
+    and opcode runs, for the E8E9 transform (libzpaq.cpp:6450-6459)."""
+    b = bytearray(O.gen_block(2, seed, n))
+    for i in range(0, max(0, n - 8), 61):
+        b[i] = 0xE8 + (i & 1)
+        b[i + 4] = 0x00 if i % 3 else 0xFF
+    for i in range(1000, min(n - 8, 1400), 2):          # candidates two apart: every rewrite changes the next test
+        b[i] = 0xE8
+    for i in range(2000, min(n - 8, 2300)):             # no three consecutive non-opcode positions: one long chain
+        b[i] = 0xFF if i % 5 == 4 else 0xE9
+    return bytes(b)
+
+
+def transform_payload(spec):
+    return exe_like(spec["seed"], spec["n"]) if spec["variant"] == "exe" else O.gen_block(spec["kind"], spec["seed"], spec["n"])

@@ -29,7 +29,7 @@ t() { local s=$(date +%s.%N); "$@" > cmd.log 2>&1; local rc=$?; local e=$(date +
 echo "== stock zpaq (CPU), -method 50, -threads 16"
 t $REF add ref.zpaq data -method 50 -threads 16
 t $REF x ref.zpaq -to out_ref -threads 16
-for T in 128 512; do
+for T in ${TS:-128 512}; do
   echo "== zpaq linked against libzpq_b200.so, -method 50, -threads $T"
   rm -rf b.zpaq out_b
   t $B200 add b.zpaq data -method 50 -threads $T
@@ -39,8 +39,10 @@ done
 echo "== cross check: stock zpaq extracts the GPU-written archive"
 t $REF x b.zpaq -to out_x -threads 16
 diff -r data out_x/data > /dev/null && echo "stock zpaq reads the GPU-written archive: identical" || echo "MISMATCH (cross)"
+if [ -z "${SKIP_SUBSET:-}" ]; then
 echo "== small subset at the CLI's default depth (-threads 16, 64 MiB): one launch per 31 blocks"
 mkdir sub && cp data/f00.txt sub/
 MBX=64; t $B200 add s.zpaq sub -method 50 -threads 16
+fi
 ls -l ref.zpaq b.zpaq | awk '{print $5, $9}'
 rm -rf "$W"

@@ -200,6 +200,12 @@ class Context:
         lib().zpq_last_timing(self._h, ms)
         return {"init_ms": ms[0], "code_ms": ms[1], "call_ms": ms[2]}
 
+    def prep_timing(self):
+        """Device time of the stages in front of the coder in the last compress_blocks call: SHA-1 + statistics, E8E9 / BWT."""
+        ms = (C.c_float * 2)()
+        lib().zpq_last_prep_timing(self._h, ms)
+        return {"analysis_ms": ms[0], "transform_ms": ms[1]}
+
     def tiers(self):
         """Blocks of the last batch per kernel tier (zpq_last_tiers): wave encoder, dec7, dec6, fast, generic, wide generic."""
         t = (C.c_uint32 * 7)()

@@ -1137,6 +1137,63 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
       std::vector<size_t> progs;
       for (size_t i = 0; i < nb; ++i)
         if (jobs[i].status == ZPQ_OK && jobs[i].out_len >= 1 && tmp[i][0] == 1) { is_prog[i] = 1; progs.push_back(i); }
+      // Blocks whose program is the plain BWT post-processor (what zpq_compress_blocks / libzpaq write for "x..,3..." methods)
+      // are inverted on the device: LF mapping by a stable radix sort, list ranking by pointer jumping (zpq_bwt.cu).
+      // Every other program runs in the host ZPAQL machine below.
+      {
+        std::vector<size_t> bw; std::vector<uint64_t> bn; std::vector<uint32_t> bidx; std::vector<size_t> bskip;
+        const char* he = getenv("ZPQ_HOST_IBWT");                          // A/B switch: 1 = every program in the host machine
+        const bool host_only = he && atoi(he) != 0;
+        for (size_t i : progs) {
+          if (host_only) break;
+          const IJob& J = jobs[i];
+          const int ph = J.hdr[4], pm = J.hdr[5];
+          if (ph != pm || ph < 20 || ph > 31 || J.seg_out.size() != 1) continue;
+          std::vector<uint8_t> code, pre;
+          if (pcomp_program(3, ph - 20, &code) != ZPQ_OK) continue;
+          pcomp_prefix(code, &pre);
+          if (J.out_len < pre.size() + 6 || memcmp(tmp[i].data(), pre.data(), pre.size()) != 0) continue;
+          const uint64_t n = J.out_len - pre.size() - 5;
+          if (n + 5 > ((uint64_t)1 << pm)) continue;
+          const uint8_t* t = tmp[i].data() + pre.size() + n + 1;
+          const uint32_t ix = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+          if (ix < 1 || ix > n) continue;
+          bw.push_back(i); bn.push_back(n); bidx.push_back(ix); bskip.push_back(pre.size());
+        }
+        size_t k = 0;
+        while (k < bw.size()) {
+          uint64_t sum = 0; size_t e2 = k;
+          while (e2 < bw.size() && e2 - k < 60000 && (e2 == k || sum + bn[e2] + 1 <= ((uint64_t)1 << 28))) sum += bn[e2++] + 1;
+          uint64_t bytes = 0;
+          std::vector<uint64_t> o_in(e2 - k), o_out(e2 - k);
+          for (size_t j = k; j < e2; ++j) { o_in[j - k] = bytes; bytes = align_up(bytes + bn[j] + 5 + 16, 256); o_out[j - k] = bytes; bytes = align_up(bytes + bn[j] + 16, 256); }
+          const uint64_t need = zpq_ibwt_workspace(sum, (int)(e2 - k));
+          if (ctx->d_xform.reserve(bytes + 256) == cudaSuccess && ctx->d_xws.reserve(need) == cudaSuccess) {
+            uint8_t* dx = (uint8_t*)ctx->d_xform.p;
+            std::vector<const uint8_t*> pin; std::vector<uint8_t*> pout;
+            for (size_t j = k; j < e2; ++j) {
+              const size_t i = bw[j];
+              CK(cudaMemcpyAsync(dx + o_in[j - k], tmp[i].data() + bskip[j], bn[j] + 5, cudaMemcpyHostToDevice, ctx->stream), "H2D BWT rows");
+              pin.push_back(dx + o_in[j - k]); pout.push_back(dx + o_out[j - k]);
+            }
+            CK(zpq_bwt_inverse(pin.data(), bn.data() + k, bidx.data() + k, pout.data(), (int)(e2 - k), ctx->d_xws.p, ctx->d_xws.cap,
+                               ctx->sm_count, ctx->stream, &ctx->launches), "inverse BWT kernels");
+            for (size_t j = k; j < e2; ++j) {
+              const size_t i = bw[j];
+              post[i].resize(bn[j]);
+              CK(cudaMemcpyAsync(post[i].data(), pout[j - k], bn[j], cudaMemcpyDeviceToHost, ctx->stream), "D2H inverse BWT");
+              post_seg[i].assign(1, bn[j]);
+            }
+            CK(cudaStreamSynchronize(ctx->stream), "inverse BWT");
+            for (size_t j = k; j < e2; ++j) is_prog[bw[j]] = 2;            // done on the device
+          }
+          else cudaGetLastError();                                        // no room: these blocks take the host machine
+          k = e2;
+        }
+        std::vector<size_t> rest;
+        for (size_t i : progs) if (is_prog[i] != 2) rest.push_back(i);
+        progs.swap(rest);
+      }
       const unsigned nt = (unsigned)std::min<size_t>(progs.size(), std::max(1u, std::min(std::thread::hardware_concurrency(), 64u)));
       std::vector<std::thread> th;
       for (unsigned t = 0; t < nt; ++t)

@@ -297,6 +297,59 @@ __global__ void __launch_bounds__(256) zpq_bwt_emit(BwtBlocks B, const u8* __res
   }
 }
 
+// ------------------------------------------------------------------ inverse BWT (what the block's PCOMP program computes)
+// Rows = the sorted suffixes of T$ (row 0 = "$"); L[row] = the byte in front of that suffix, the row `idx` holds the
+// end-of-string mark.  A stable sort of the rows by L (the mark first) is the LF mapping: the row at sorted position p is
+// the one whose suffix, extended by one byte to the left, is row p -- read the other way round, psi(p) = the row that follows p
+// in text order.  The text is the list idx -> psi(idx) -> ... -> 0; list ranking by pointer jumping gives every row its
+// distance to row 0 and so its place in the output.
+struct IbwtBlocks {
+  const u8* const* in;                 // BWT bytes of block b: rows 0 .. n, then the index (4 bytes)
+  u8* const* out;                      // n bytes
+  const u32* off;                      // nb + 1 row offsets (block b has n_b + 1 rows)
+  const u32* idx;                      // row of the end-of-string mark, per block
+  int nb;
+};
+
+__global__ void __launch_bounds__(256) zpq_ibwt_setup(IbwtBlocks B, u32 rows, u64* __restrict__ key, u32* __restrict__ val) {
+  for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const int b = block_of(B.off, B.nb, r);
+    const u32 o = __ldg(B.off + b), j = r - o;
+    const u32 sym = j == __ldg(B.idx + b) ? 0u : (u32)B.in[b][j] + 1u;
+    key[r] = (u64)o << 32 | (u64)sym;
+    val[r] = r;
+  }
+}
+
+// psi from the sorted rows; row 0 of every block ends its list
+__global__ void __launch_bounds__(256) zpq_ibwt_links(IbwtBlocks B, u32 rows, const u64* __restrict__ key, const u32* __restrict__ val,
+                                                      u32* __restrict__ nxt, u32* __restrict__ dst) {
+  for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < rows; p += gridDim.x * blockDim.x) {
+    const u32 o = (u32)(key[p] >> 32);
+    const bool last = p == o;
+    nxt[p] = last ? p : val[p];
+    dst[p] = last ? 0u : 1u;
+  }
+}
+
+__global__ void __launch_bounds__(256) zpq_ibwt_jump(u32 rows, const u32* __restrict__ nxt, const u32* __restrict__ dst, u32* __restrict__ nxt2, u32* __restrict__ dst2) {
+  for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < rows; p += gridDim.x * blockDim.x) {
+    const u32 q = nxt[p];
+    dst2[p] = dst[p] + dst[q];
+    nxt2[p] = nxt[q];
+  }
+}
+
+__global__ void __launch_bounds__(256) zpq_ibwt_emit(IbwtBlocks B, u32 rows, const u32* __restrict__ dst) {
+  for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const int b = block_of(B.off, B.nb, r);
+    const u32 o = __ldg(B.off + b), n = __ldg(B.off + b + 1) - o - 1u, j = r - o;
+    if (j == __ldg(B.idx + b)) continue;
+    const u32 d = dst[r];
+    if (d < n) B.out[b][n - 1u - d] = B.in[b][j];
+  }
+}
+
 inline u64 al256(u64 x) { return (x + 255) & ~(u64)255; }
 inline int bitlen(u64 x) { int r = 0; for (; x; x >>= 1) ++r; return r; }
 
@@ -444,5 +497,76 @@ extern "C" cudaError_t zpq_e8e9_forward(const uint8_t* const* in, uint8_t* const
   if (gx > (u64)sm_count * 16) gx = (u64)sm_count * 16;
   zpq_e8e9_kernel<<<dim3((unsigned)gx, (unsigned)nb), 128, 0, st>>>(d_in, d_out, d_len, slice);
   if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ inverse BWT driver
+extern "C" uint64_t zpq_ibwt_workspace(uint64_t total_rows, int nb) {
+  const u64 n = total_rows ? total_rows : 1;
+  const u64 tiles = (n + TILE - 1) / TILE;
+  return al256(n * 8) * 2 + al256(n * 4) * 6 + al256(tiles * 256 * 4) + al256((tiles + 2) * 4 + 4096) +
+         al256((u64)(nb + 1) * 4) + al256((u64)nb * 4) + al256((u64)nb * 8) * 2 + 256;
+}
+
+// in[b]: DEVICE pointer to the n_b + 5 bytes a BWT block's model emits after the program (rows, then the index);
+// n[b]: payload length; idx[b]: the index (host, already range-checked: 1 .. n_b); out[b]: DEVICE pointer, n_b bytes.
+extern "C" cudaError_t zpq_bwt_inverse(const uint8_t* const* in, const uint64_t* n, const uint32_t* idx, uint8_t* const* out, int nb,
+                                       void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches) {
+  if (nb <= 0) return cudaSuccess;
+  if (nb > 65535) return cudaErrorInvalidValue;
+  u64 total = 0, maxn = 0;
+  for (int b = 0; b < nb; ++b) { total += n[b] + 1; maxn = n[b] > maxn ? n[b] : maxn; }
+  if (total >= ((u64)1 << 31) || zpq_ibwt_workspace(total, nb) > ws_bytes) return cudaErrorInvalidValue;
+  const u32 rows = (u32)total;
+  const u64 tiles1 = ((u64)rows + TILE - 1) / TILE;
+  u8* p = (u8*)ws;
+  auto take = [&](u64 bytes) { u8* r = p; p += al256(bytes); return r; };
+  u64* keyb[2] = {(u64*)take((u64)rows * 8), (u64*)take((u64)rows * 8)};
+  u32* valb[2] = {(u32*)take((u64)rows * 4), (u32*)take((u64)rows * 4)};
+  u32* nxtb[2] = {(u32*)take((u64)rows * 4), (u32*)take((u64)rows * 4)};
+  u32* dstb[2] = {(u32*)take((u64)rows * 4), (u32*)take((u64)rows * 4)};
+  u32* counts = (u32*)take(tiles1 * 256 * 4);
+  u32* partial = (u32*)take((tiles1 + 2) * 4 + 4096);
+  u32* d_off = (u32*)take((u64)(nb + 1) * 4);
+  u32* d_idx = (u32*)take((u64)nb * 4);
+  const u8** d_in = (const u8**)take((u64)nb * 8);
+  u8** d_out = (u8**)take((u64)nb * 8);
+  u32* h_off = new u32[nb + 1];
+  h_off[0] = 0;
+  for (int b = 0; b < nb; ++b) h_off[b + 1] = h_off[b] + (u32)n[b] + 1u;
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(d_off, h_off, (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) { delete[] h_off; return e; }
+  if ((e = cudaMemcpyAsync(d_idx, idx, (size_t)nb * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) { delete[] h_off; return e; }
+  if ((e = cudaMemcpyAsync(d_in, in, (size_t)nb * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) { delete[] h_off; return e; }
+  if ((e = cudaMemcpyAsync(d_out, out, (size_t)nb * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) { delete[] h_off; return e; }
+  e = cudaStreamSynchronize(st);
+  delete[] h_off;
+  if (e != cudaSuccess) return e;
+  IbwtBlocks B; B.in = d_in; B.out = d_out; B.off = d_off; B.idx = d_idx; B.nb = nb;
+  const int maxg = sm_count * 8;
+  auto grid = [&](u32 m) { const u32 g = (m + 255) / 256; return (int)(g < (u32)maxg ? (g ? g : 1) : (u32)maxg); };
+  u64 nl = 0;
+  zpq_ibwt_setup<<<grid(rows), 256, 0, st>>>(B, rows, keyb[0], valb[0]); ++nl;
+  // stable sort of the rows by (block, symbol): 9 symbol bits, then the bits of the block's first row
+  int kcur = 0;
+  const u32 tiles = (u32)tiles1;
+  const int bits_hi = bitlen(rows - 1);
+  for (int part = 0; part < 2; ++part) {
+    const int nbits = part == 0 ? 9 : bits_hi, base = part == 0 ? 0 : 32;
+    for (int sh = 0; sh < nbits; sh += 8) {
+      zpq_radix_hist<<<tiles, 256, 0, st>>>(keyb[kcur], rows, base + sh, counts, tiles); ++nl;
+      if ((e = scan_u32<false, false>(counts, tiles * 256u, counts, partial, st, &nl)) != cudaSuccess) return e;
+      zpq_radix_scatter<<<tiles, 256, 0, st>>>(keyb[kcur], valb[kcur], keyb[kcur ^ 1], valb[kcur ^ 1], rows, base + sh, counts, tiles); ++nl;
+      kcur ^= 1;
+    }
+  }
+  zpq_ibwt_links<<<grid(rows), 256, 0, st>>>(B, rows, keyb[kcur], valb[kcur], nxtb[0], dstb[0]); ++nl;
+  int lc = 0;
+  for (u64 span = 1; span < maxn + 1; span <<= 1) {
+    zpq_ibwt_jump<<<grid(rows), 256, 0, st>>>(rows, nxtb[lc], dstb[lc], nxtb[lc ^ 1], dstb[lc ^ 1]); ++nl;
+    lc ^= 1;
+  }
+  zpq_ibwt_emit<<<grid(rows), 256, 0, st>>>(B, rows, dstb[lc]); ++nl;
+  if (launches) *launches += nl;
   return cudaGetLastError();
 }

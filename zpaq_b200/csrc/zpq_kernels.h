@@ -35,6 +35,10 @@ cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant);
 uint64_t zpq_bwt_workspace(uint64_t total, int nb);
 cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, int nb,
                             void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches);
+// inverse BWT of blocks whose PCOMP program is the BWT post-processor: in[b] = the n[b] + 5 model bytes after the program
+uint64_t zpq_ibwt_workspace(uint64_t total_rows, int nb);
+cudaError_t zpq_bwt_inverse(const uint8_t* const* in, const uint64_t* n, const uint32_t* idx, uint8_t* const* out, int nb,
+                            void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches);
 cudaError_t zpq_e8e9_forward(const uint8_t* const* in, uint8_t* const* out, const uint64_t* len, int nb, void* ws,
                              int sm_count, cudaStream_t st, uint64_t* launches);
 unsigned long long zpq_code2_signature(const ZFast* F);
