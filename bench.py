@@ -6,6 +6,7 @@ Contract (see the task statement): one JSON line on rank 0.
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # libzpaq 7.15 on the host cores
   python bench.py --config m4_256 | chain17_512            # BASELINE configs[1] / configs[3] (not the headline line)
+  python bench.py --config bwt_256                         # the BWT path, with the suffix sorter's own roofline
 
 Workload (BASELINE.json configs[2], the default): 1 GiB of synthetic 1 MiB-class blocks
 (payload 1 044 480 B = 2^20 - 4096, what `zpaq -method 50` produces) coded with
@@ -48,6 +49,7 @@ CHAIN17 = "x0,0ci1,1,1,1,1,1,1,1c256c8,0,255c16,0,255,255aw1c0,0,255,1001,255c0,
 CONFIGS = {
     "m5_1g": ("5", "50", 1 << 30, 1, "BASELINE configs[2]: -method 5 (23-component makeConfig CM chain), 1 GiB of 1 MiB-class blocks per GPU, 'mixed' LCG text"),
     "m4_256": ("4", "40", 256 * BLOCK, 0, "BASELINE configs[1]: -method 4 (8-component ICM/ISSE chain + MATCH + MIX), 256 x 1 MiB-class 'text' blocks"),
+    "bwt_256": ("x0,3ci1", "x0,3ci1", 256 * BLOCK, 0, "SURVEY.md 8(f)-4 (not a BASELINE config): BWT pre-processing on the device (batched suffix sort, zpq_bwt.cu) + 2-component ICM/ISSE model, 256 x 1 MiB-class 'text' blocks; decompression inverts the BWT on the device"),
     "chain17_512": (CHAIN17, CHAIN17, 1 << 29, 1, "BASELINE configs[3]: custom 17-component chain (8-deep ISSE chain, 16-input MIX with 2^16 weight sets), 512 MiB of 1 MiB-class 'mixed' blocks"),
 }
 KIND_NAME = {0: "text", 1: "mixed", 2: "random"}
@@ -495,6 +497,7 @@ def main():
         if rc:
             raise SystemExit("zpq_compress_blocks failed: %d %s" % (rc, ctx.last_error()))
         tc = ctx.timing()
+        tp = ctx.prep_timing()
         # archive = blocks back to back (what zpaq's writer thread appends, zpaq.cpp:1968)
         pos = 0
         src = host_arc.numpy(); dst = arc_cat.numpy()
@@ -514,7 +517,7 @@ def main():
             raise SystemExit("round trip size mismatch")
         return {"wall_c": t1 - t0, "wall_d": t3 - t2, "dev_c": (tc["init_ms"] + tc["code_ms"]) / 1e3,
                 "dev_d": (td["init_ms"] + td["code_ms"]) / 1e3, "code_c": tc["code_ms"] / 1e3, "code_d": td["code_ms"] / 1e3,
-                "arc_bytes": pos, "wall": t3 - t0}
+                "arc_bytes": pos, "wall": t3 - t0, "xf_s": tp["transform_ms"] / 1e3, "xf_bytes": float(tp["transform_alg_bytes"])}
 
     def barrier():
         torch.cuda.synchronize()
@@ -547,7 +550,7 @@ def main():
     sampler.start()
     launches0 = ctx.launch_count()
     barrier()
-    acc = {"wall_c": 0.0, "wall_d": 0.0, "dev_c": 0.0, "dev_d": 0.0, "code_c": 0.0, "code_d": 0.0}
+    acc = {"wall_c": 0.0, "wall_d": 0.0, "dev_c": 0.0, "dev_d": 0.0, "code_c": 0.0, "code_d": 0.0, "xf_s": 0.0, "xf_bytes": 0.0}
     t_begin = time.perf_counter()
     done = 0
     for k in range(args.steps):
@@ -577,7 +580,10 @@ def main():
     mb = tot_bytes / 1e6
 
     if rank == 0:
-        hdr = Z.model_from_method(METHOD, bytes(host_in.numpy()[:sizes[0]]))
+        try:
+            hdr = Z.model_from_method(METHOD, bytes(host_in.numpy()[:sizes[0]]))
+        except Z.ZpqError:
+            hdr = Z.block_plan(METHOD, sizes[0])[0]          # a method that pre-processes the payload (BWT)
         balg = alg_bytes_per_input_byte(hdr, BLOCK)
         arena_bytes = Z.model_bytes(hdr)
         peaks = {}
@@ -645,6 +651,12 @@ def main():
                          "kernel": "encode + decode coding kernels (see DESIGN.md section 3)",
                          "kernel_variants": {k: v for k, v in os.environ.items() if k.startswith("ZPQ_") and k != "ZPQ_BENCH_BUDGET_S"},
                          "note": "latency/issue bound, not bandwidth bound (see profiles/ and DESIGN.md section 6)"},
+            "transform": None if acc["xf_bytes"] <= 0 else {
+                "kernel": "suffix sort of the BWT (zpq_bwt.cu: radix passes + regrouping over the still-unsorted suffixes), rank 0",
+                "ms_per_step": acc["xf_s"] * 1e3 / done, "MBps": nbytes * done / 1e6 / acc["xf_s"],
+                "alg_bytes_per_input_byte": acc["xf_bytes"] / (nbytes * done),
+                "roofline": {"bound": "hbm", "achieved": acc["xf_bytes"] / acc["xf_s"] / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": acc["xf_bytes"] / acc["xf_s"] / 1e9 / peak, "traffic": None}},
             "cpu_baseline": cpu, "bit_exact_vs_reference": bit_exact, "clocks": clocks,
             "archive_ratio": r["arc_bytes"] / nbytes, "setup_s": gen_s, "warmup_s": warm_s, "total_s": time.time() - T_START,
         }

@@ -127,6 +127,9 @@ int zpq_last_timing(const zpq_ctx* ctx, float ms[3]);
 /* Device time (ms) of the stages in front of the coder in the last zpq_compress_blocks[_dev] call (both are part of
  * zpq_last_timing's [0]): [0] SHA-1 + level-5 statistics, [1] E8E9 / BWT pre-processing. */
 int zpq_last_prep_timing(const zpq_ctx* ctx, float ms[2]);
+/* Algorithmic HBM bytes of the suffix-sorting kernels of that call (sort passes x 32 bytes per still-unsorted suffix + the
+ * per-round bookkeeping), the numerator of their roofline. */
+uint64_t zpq_last_transform_bytes(const zpq_ctx* ctx);
 /* Number of kernel launches issued by this context so far. */
 uint64_t zpq_launch_count(const zpq_ctx* ctx);
 /* Diagnostics: blocks of the last batch coded by each kernel tier: [0] wavefront encoder (zpq_kernels5.cu),

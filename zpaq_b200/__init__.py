@@ -62,7 +62,7 @@ EXPORTS = ["zpq_abi_version", "zpq_create", "zpq_destroy", "zpq_strerror", "zpq_
            "zpq_encode_blocks", "zpq_decode_blocks", "zpq_encode_blocks_dev", "zpq_decode_blocks_dev",
            "zpq_last_timing", "zpq_launch_count", "zpq_compress_blocks", "zpq_decompress_archive",
            "zpq_compress_bound", "zpq_postprocess_block", "zpq_model_describe", "zpq_last_tiers",
-           "zpq_compress_blocks_dev", "zpq_analyze_dev", "zpq_scan_archive", "zpq_header_from_stats", "zpq_block_plan", "zpq_last_prep_timing"]
+           "zpq_compress_blocks_dev", "zpq_analyze_dev", "zpq_scan_archive", "zpq_header_from_stats", "zpq_block_plan", "zpq_last_prep_timing", "zpq_last_transform_bytes"]
 
 _lib = None
 
@@ -92,6 +92,8 @@ def lib():
             f.argtypes = [vp, i32, C.POINTER(Job)]
         L.zpq_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
         L.zpq_last_prep_timing.argtypes = [vp, C.POINTER(C.c_float)]
+        L.zpq_last_transform_bytes.argtypes = [vp]
+        L.zpq_last_transform_bytes.restype = u64
         L.zpq_launch_count.argtypes = [vp]
         L.zpq_last_tiers.argtypes = [vp, C.POINTER(C.c_uint32)]
         L.zpq_launch_count.restype = u64
@@ -204,7 +206,7 @@ class Context:
         """Device time of the stages in front of the coder in the last compress_blocks call: SHA-1 + statistics, E8E9 / BWT."""
         ms = (C.c_float * 2)()
         lib().zpq_last_prep_timing(self._h, ms)
-        return {"analysis_ms": ms[0], "transform_ms": ms[1]}
+        return {"analysis_ms": ms[0], "transform_ms": ms[1], "transform_alg_bytes": int(lib().zpq_last_transform_bytes(self._h))}
 
     def tiers(self):
         """Blocks of the last batch per kernel tier (zpq_last_tiers): wave encoder, dec7, dec6, fast, generic, wide generic."""

@@ -58,7 +58,7 @@ struct Req {
 // launch is bound by the latency of one block, so waiting a few milliseconds for all of them costs nothing): ZPQ_SHIM_WINDOW_MS
 int window_ms() { static const int ms = [] { const char* e = getenv("ZPQ_SHIM_WINDOW_MS"); const int v = e ? atoi(e) : 100; return v < 0 ? 0 : (v > 1000 ? 1000 : v); }(); return ms; }
 
-int max_wait_ms() { static const int ms = [] { const char* e = getenv("ZPQ_SHIM_MAX_WAIT_MS"); const int v = e ? atoi(e) : 3000; return v < 0 ? 0 : (v > 10000 ? 10000 : v); }(); return ms; }
+int max_wait_ms() { static const int ms = [] { const char* e = getenv("ZPQ_SHIM_MAX_WAIT_MS"); const int v = e ? atoi(e) : 30000; return v < 0 ? 0 : (v > 600000 ? 600000 : v); }(); return ms; }
 
 struct Batcher {
   std::mutex mu; std::condition_variable cv_submit, cv_done;
@@ -77,7 +77,7 @@ struct Batcher {
         // A launch is bound by the latency of ONE block (about ten seconds for a 1 MiB block at level 5, whatever the
         // batch size), so a batch should be everything the caller will supply: keep waiting in steps of
         // ZPQ_SHIM_WINDOW_MS (100 ms: zpaq's reader thread fragments and hashes at ~100 MB/s, a block every ~10 ms) while
-        // the queue is still growing, at most ZPQ_SHIM_MAX_WAIT_MS (3 s) in all.  Measured: profiles/r02q_cli_threads.log
+        // the queue is still growing, at most ZPQ_SHIM_MAX_WAIT_MS (30 s) in all.  Measured: profiles/r02q_cli_threads.log
         const auto t0 = std::chrono::steady_clock::now();
         size_t seen = queue.size();
         for (;;) {

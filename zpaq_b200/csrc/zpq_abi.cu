@@ -66,6 +66,7 @@ struct zpq_ctx {
   std::string err;
   float ms[3] = {0, 0, 0};
   float ms_prep = 0;           // device time of the last analysis pass (SHA-1, gap statistics); added to ms[0] by the whole-block calls
+  uint64_t xform_bytes = 0;    // algorithmic HBM bytes of the last pre-processing pass (zpq_bwt_forward)
   float ms_xform = 0;          // device time of the last pre-processing pass (E8E9, BWT: zpq_bwt.cu); added to ms[0] as well
   DevBuf d_xform, d_xws;       // transformed payloads; workspace of the suffix sorter
   uint64_t launches = 0;
@@ -710,6 +711,8 @@ int zpq_last_prep_timing(const zpq_ctx* ctx, float ms[2]) {
   return ZPQ_OK;
 }
 
+uint64_t zpq_last_transform_bytes(const zpq_ctx* ctx) { return ctx ? ctx->xform_bytes : 0; }
+
 uint64_t zpq_launch_count(const zpq_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int zpq_last_tiers(const zpq_ctx* ctx, uint32_t tiers[7]) {
@@ -828,7 +831,7 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
   // ---- pre-processing on the device (LZBuffer level 3 and e8e9(), libzpaq.cpp:6450-6459, 6630-6658): zpq_bwt.cu ----
   std::vector<const uint8_t*> d_model_in(d_data);                // what goes through the model after the prefix
   std::vector<uint64_t> model_len(len, len + nblk);
-  ctx->ms_xform = 0;
+  ctx->ms_xform = 0; ctx->xform_bytes = 0;
   {
     uint64_t tot = 0;
     std::vector<uint64_t> off_e8(nblk, 0), off_bwt(nblk, 0);
@@ -878,7 +881,7 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
             ctx->err = "Out of memory";
           }
           else {
-            CK(zpq_bwt_forward(bin.data(), blen.data(), bout.data(), (int)(e - k), ctx->d_xws.p, ctx->d_xws.cap, ctx->sm_count, stream, &ctx->launches), "BWT kernels");
+            CK(zpq_bwt_forward(bin.data(), blen.data(), bout.data(), (int)(e - k), ctx->d_xws.p, ctx->d_xws.cap, ctx->sm_count, stream, &ctx->launches, &ctx->xform_bytes), "BWT kernels");
             for (size_t j = k; j < e; ++j) { const int i = ids[j]; d_model_in[i] = dx + off_bwt[i]; model_len[i] = len[i] + 5; }
           }
           k = e;

@@ -386,8 +386,10 @@ extern "C" uint64_t zpq_bwt_workspace(uint64_t total, int nb) {
 }
 
 // in[b] / out[b]: DEVICE pointers (host arrays of them); len[b] host.  out[b] receives len[b] + 5 bytes.
+// alg_bytes (optional): algorithmic HBM bytes of the kernels launched, for the roofline: per sort pass 8 (histogram read) +
+// 12 + 12 (scatter read + write) per active suffix, per round 100 more (keys, heads, two scans, update, compaction).
 extern "C" cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, int nb,
-                                       void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches) {
+                                       void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches, uint64_t* alg_bytes) {
   if (nb <= 0) return cudaSuccess;
   if (nb > 65535) return cudaErrorInvalidValue;
   u64 total = 0;
@@ -428,7 +430,7 @@ extern "C" cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t*
   BwtBlocks B; B.in = d_in; B.out = d_out; B.off = d_off; B.nb = nb;
   const int maxg = sm_count * 8;
   auto grid = [&](u32 m) { const u32 g = (m + 255) / 256; return (int)(g < (u32)maxg ? (g ? g : 1) : (u32)maxg); };
-  u64 nl = 0;
+  u64 nl = 0, ab = (u64)n * 24;                  // set-up: payload read, text / block id / key / value / slot written
   int kcur = 0, scur = 0;                        // key / value buffer and slot buffer that hold the active list
   u32 m = n;
   if (n) { zpq_bwt_setup<<<grid(n), 256, 0, st>>>(B, n, txt, bid, keyb[0], valb[0], slotb[0]); ++nl; }
@@ -446,9 +448,11 @@ extern "C" cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t*
         if ((e = scan_u32<false, false>(counts, tiles * 256u, counts, partial, st, &nl)) != cudaSuccess) return e;
         zpq_radix_scatter<<<tiles, 256, 0, st>>>(keyb[kcur], valb[kcur], keyb[kcur ^ 1], valb[kcur ^ 1], m, base + sh, counts, tiles);
         ++nl;
+        ab += (u64)m * 32;
         kcur ^= 1;
       }
     }
+    ab += (u64)m * 100;
     // ---- regroup ----
     zpq_bwt_heads<<<grid(m), 256, 0, st>>>(keyb[kcur], slotb[scur], m, t1); ++nl;
     if ((e = scan_u32<true, true>(t1, m, t1, partial, st, &nl)) != cudaSuccess) return e;
@@ -472,8 +476,10 @@ extern "C" cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t*
     if (g.x * (unsigned)nb > (unsigned)maxg * 4u) g.x = ((unsigned)maxg * 4u + nb - 1) / nb;
     if (g.x == 0) g.x = 1;
     zpq_bwt_emit<<<g, 256, 0, st>>>(B, txt, sa); ++nl;
+    ab += (u64)n * 6;
   }
   if (launches) *launches += nl;
+  if (alg_bytes) *alg_bytes += ab;
   return cudaGetLastError();
 }
 

@@ -34,7 +34,7 @@ cudaError_t zpq_launch_wave(const ZWaveArgs* w, cudaStream_t st, int variant);
 // zpq_bwt.cu: forward transforms in front of the model; in / out are HOST arrays of DEVICE pointers, len is host memory
 uint64_t zpq_bwt_workspace(uint64_t total, int nb);
 cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, int nb,
-                            void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches);
+                            void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches, uint64_t* alg_bytes);
 // inverse BWT of blocks whose PCOMP program is the BWT post-processor: in[b] = the n[b] + 5 model bytes after the program
 uint64_t zpq_ibwt_workspace(uint64_t total_rows, int nb);
 cudaError_t zpq_bwt_inverse(const uint8_t* const* in, const uint64_t* n, const uint32_t* idx, uint8_t* const* out, int nb,
