@@ -26,9 +26,11 @@ PY
 echo "== host: $(nproc) cpus, cgroup $(cat /sys/fs/cgroup/cpu.max 2>/dev/null)"; nvidia-smi --query-gpu=name --format=csv,noheader
 cd "$W"
 t() { local s=$(date +%s.%N); "$@" > cmd.log 2>&1; local rc=$?; local e=$(date +%s.%N); tail -2 cmd.log | tr '\n' ' '; echo; python -c "import sys; d=float(sys.argv[2])-float(sys.argv[1]); print('rc=%s seconds=%.2f MBps=%.2f ::' % (sys.argv[3], d, float(sys.argv[4])*1.048576/d), ' '.join(sys.argv[5:]))" $s $e $rc ${MBX:-$MB} "$@"; }
+if [ -z "${SKIP_STOCK:-}" ]; then
 echo "== stock zpaq (CPU), -method 50, -threads 16"
 t $REF add ref.zpaq data -method 50 -threads 16
 t $REF x ref.zpaq -to out_ref -threads 16
+fi
 for T in ${TS:-128 512}; do
   echo "== zpaq linked against libzpq_b200.so, -method 50, -threads $T"
   rm -rf b.zpaq out_b
@@ -36,13 +38,15 @@ for T in ${TS:-128 512}; do
   t $B200 x b.zpaq -to out_b -threads $T
   diff -r data out_b/data > /dev/null && echo "extracted files identical to the input (T=$T)" || echo "MISMATCH (T=$T)"
 done
+if [ -z "${SKIP_STOCK:-}" ]; then
 echo "== cross check: stock zpaq extracts the GPU-written archive"
 t $REF x b.zpaq -to out_x -threads 16
 diff -r data out_x/data > /dev/null && echo "stock zpaq reads the GPU-written archive: identical" || echo "MISMATCH (cross)"
+fi
 if [ -z "${SKIP_SUBSET:-}" ]; then
 echo "== small subset at the CLI's default depth (-threads 16, 64 MiB): one launch per 31 blocks"
 mkdir sub && cp data/f00.txt sub/
 MBX=64; t $B200 add s.zpaq sub -method 50 -threads 16
 fi
-ls -l ref.zpaq b.zpaq | awk '{print $5, $9}'
+ls -l ref.zpaq b.zpaq 2>/dev/null | awk '{print $5, $9}'
 rm -rf "$W"
