@@ -32,38 +32,29 @@ def test_blocks_equal_the_reference_goldens(ctx, method, cases):
 
 
 def test_full_size_batch_against_the_live_reference(ctx):
-    """48 blocks x 1 044 480 B of three kinds through BWT in one call (one index space for all suffixes), two of them and one
-    E8E9 + BWT block compared with the unmodified reference, all of them decoded again."""
+    """48 blocks x 1 044 480 B of three kinds through BWT in one call (one index space for all suffixes), an E8E9 + BWT block and
+    a block of another size class (1.5 MiB: ph = pm = 21, suffix ranks of 21 bits); some of them compared with the unmodified
+    reference, seven decoded again in ONE call (a launch costs the latency of its longest block, whatever it holds).  The
+    program variant of blocks above 16 MiB is covered by the `x5,...` goldens on small payloads: one block of that size alone
+    is minutes of coder latency."""
     import refpy as R
     n = (1 << 20) - 4096
     pays = [O.gen_block(k % 3, 7000 + k, n) for k in range(48)]
     blocks = ctx.compress_blocks("x0,3ci1", pays)
+    e = exe_like(99, n)
+    be = ctx.compress_blocks("x0,7ci1", [e])[0]
+    big = O.gen_block(0, 4242, 3 << 19)
+    bb = ctx.compress_blocks("31,200,1", [big])[0]
+    hdr = O.parse_blocks(bb)[0].header
+    assert hdr[4] == 21 and hdr[5] == 21
     if R.available():
         for k in (0, 1):
             assert blocks[k] == R.compress_block(pays[k], "x0,3ci1"), k
-    out, nb = ctx.decompress_archive(b"".join(blocks[:6]), 6 * n)
-    assert nb == 6 and out == b"".join(pays[:6])
-    e = exe_like(99, n)
-    be = ctx.compress_blocks("x0,7ci1", [e])[0]
-    if R.available():
         assert be == R.compress_block(e, "x0,7ci1")
-    out, nb = ctx.decompress_archive(be, n)
-    assert out == e
-
-
-def test_block_of_another_size_class(ctx):
-    """size class 1 (one block of 1.5 MiB): ph = pm = 21, suffix ranks of 21 bits.  (The program variant of blocks above 16 MiB
-    is covered by the `x5,...` goldens on small payloads: one block of that size alone is minutes of coder latency.)"""
-    import refpy as R
-    n = 3 << 19
-    p = O.gen_block(0, 4242, n)
-    b = ctx.compress_blocks("31,200,1", [p])[0]
-    hdr = O.parse_blocks(b)[0].header
-    assert hdr[4] == 21 and hdr[5] == 21
-    if R.available():
-        assert b == R.compress_block(p, "31,200,1")
-    out, nb = ctx.decompress_archive(b, n)
-    assert nb == 1 and out == p
+        assert bb == R.compress_block(big, "31,200,1")
+    want = b"".join(pays[:5]) + e + big
+    out, nb = ctx.decompress_archive(b"".join(blocks[:5]) + be + bb, len(want))
+    assert nb == 7 and out == want
 
 
 def test_degenerate_payloads(ctx):

@@ -1065,7 +1065,12 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
   std::vector<char> stored(nb, 0);
   bool any_stored = false;
   for (size_t i = 0; i < nb; ++i) if (jobs[i].hlen > 6 && jobs[i].hdr[6] == 0) { stored[i] = 1; any_stored = true; }
-  bool direct = all_hinted && !any_stored;
+  // a header that announces a post-processor machine (ph / pm: BWT and LZ77 blocks) means the model output is a PCOMP program
+  // plus transformed bytes, never the payload itself: such an archive goes through staging at once instead of finding out
+  // by a wasted decode into the caller's buffer
+  bool any_pcomp = false;
+  for (size_t i = 0; i < nb; ++i) if (jobs[i].hlen > 6 && (jobs[i].hdr[4] || jobs[i].hdr[5])) any_pcomp = true;
+  bool direct = all_hinted && !any_stored && !any_pcomp;
   if (direct) {
     uint64_t p = 0;
     for (size_t i = 0; i < nb; ++i) { pos[i] = p; p += (uint64_t)hint[i]; }
@@ -1111,7 +1116,9 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
       J.first_byte = tmp[i].empty() ? -1 : tmp[i][0];
     }
     std::vector<uint64_t> cap(nb);
-    for (size_t i = 0; i < nb; ++i) cap[i] = hint[i] >= 0 ? (uint64_t)hint[i] + 1 : (uint64_t)4 << 20;
+    // size hint + flag byte + room for a PCOMP program (<= 64 KiB + 3) and a transform's trailer (BWT: 5 bytes): a block with
+    // a program must not be decoded twice only because its program did not fit the payload's size
+    for (size_t i = 0; i < nb; ++i) cap[i] = hint[i] >= 0 ? (uint64_t)hint[i] + 1 + 66000 : (uint64_t)4 << 20;
     while (!pending.empty()) {
       std::vector<IJob> sub;
       for (size_t i : pending) {

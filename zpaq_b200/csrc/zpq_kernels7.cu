@@ -679,6 +679,9 @@ static const unsigned long long kSig7L5 = 1ull | 1ull << 3 | 1ull << 6 | 1ull <<
 // BASELINE configs[3]: the 17-component chain (8 ISSE levels, one 16-input MIX)
 static const unsigned long long kSig7C17 = 1ull | 1ull << 3 | 1ull << 6 | 1ull << 9 | 1ull << 12 | 1ull << 15 | 1ull << 18 | 1ull << 21 | 2ull << 24;
 
+// the model behind a BWT ("ci1": an order-0 ICM and one order-1 ISSE link, libzpaq.cpp:7623, 7644): one chain level, no mixer
+static const unsigned long long kSig7Bwt = 1ull;
+
 template <unsigned long long SIG>
 static cudaError_t launch7(const ZKernelArgs* a, int ctas, int threads, size_t smem, int pw_bytes, int teams, cudaStream_t st) {
   static bool attr_set = false;
@@ -705,10 +708,11 @@ extern "C" cudaError_t zpq_launch_dec7(const ZKernelArgs* a, int nblk, int sm_co
   if (sig == kSig7L5) return launch7<kSig7L5>(a, ctas, th, smem, pw_bytes, teams, st);
   if (sig == kSig7L4) return launch7<kSig7L4>(a, ctas, th, smem, pw_bytes, teams, st);
   if (sig == kSig7C17) return launch7<kSig7C17>(a, ctas, th, smem, pw_bytes, teams, st);
+  if (sig == kSig7Bwt) return launch7<kSig7Bwt>(a, ctas, th, smem, pw_bytes, teams, st);
   return cudaErrorInvalidValue;        // zpq_dec7_takes(sig) is false: the caller uses zpq_kernels6.cu
 }
 
-// Step signatures this kernel is instantiated for: the two makeConfig families and the 17-component chain.  Any other
+// Step signatures this kernel is instantiated for: the two makeConfig families, the 17-component chain and the BWT model.  Any other
 // step list is decoded by the round-1 two-warp kernel, whose generic instantiation reads the list at run time (a fully
 // run-time step list here exceeds ptxas' predicate budget: every step kind of every step becomes a live predicate).
-extern "C" int zpq_dec7_takes(unsigned long long sig) { return sig == kSig7L5 || sig == kSig7L4 || sig == kSig7C17; }
+extern "C" int zpq_dec7_takes(unsigned long long sig) { return sig == kSig7L5 || sig == kSig7L4 || sig == kSig7C17 || sig == kSig7Bwt; }
