@@ -59,12 +59,15 @@ def test_zpaq_extract_of_stored_blocks_needs_no_gpu(tmp_path):
 
 @need_cli
 @pytest.mark.gpu
-@pytest.mark.parametrize("method", ["4", "5"])
+@pytest.mark.parametrize("method", ["4", "5", "3"])
 def test_zpaq_add_on_gpu_extracts_with_stock_zpaq(tmp_path, method):
-    """`zpaq add -method 4/5` through the GPU library; the archive is read back by the stock reference CLI."""
+    """`zpaq add -method 4/5` through the GPU library; the archive is read back by the stock reference CLI.  With `-method 3`
+    zpaq asks for BWT on this (redundant) input: suffix sorting, the PCOMP program and the two-component model all run in the
+    GPU library (zpq_bwt.cu)."""
     names = _files(tmp_path)
-    rc, out = _run(B200, ["add", "g.zpaq"] + names + ["-method", method, "-threads", "8"], tmp_path)
+    rc, out = _run(B200, ["add", "g.zpaq"] + names + ["-method", method, "-threads", "8"], tmp_path, log=True)
     assert rc == 0, out
+    assert "-> GPU, status 0" in out, out
     rc, out = _run(REF, ["x", "g.zpaq", "-to", "og"], tmp_path)
     assert rc == 0, out
     for n in names:

@@ -163,6 +163,21 @@ struct Batcher {
 
 Batcher& batcher() { static Batcher* b = new Batcher(); return *b; }
 
+// which methods the GPU library takes is decided by the library itself: zpq_model_from_method for the methods that feed the
+// model with the payload, zpq_block_plan for those that put a transform in front of it (BWT, E8E9: zpq_bwt.cu).  Store and
+// LZ77 selections come back as ZPQ_E_METHOD.
+int probe_method(const char* method, const uint8_t* data, uint64_t n, uint8_t* hdr, int cap, int* hlen) {
+  int rc = zpq_model_from_method(method, data, n, hdr, cap, hlen);
+  if (rc == ZPQ_E_METHOD) {
+    static thread_local uint8_t prefix[70000];
+    int prep = 0, plen = 0;
+    const int32_t g[2] = {0, 0};
+    const int rp = zpq_block_plan(method, n, g, hdr, cap, hlen, &prep, prefix, (int)sizeof(prefix), &plen);
+    if (rp == ZPQ_OK && prep != 0) rc = ZPQ_OK;
+  }
+  return rc;
+}
+
 // does the CUDA library code blocks of this (valid, modelled) header?
 bool gpu_takes(const uint8_t* hdr, int hlen) {
   uint32_t info[8];
@@ -172,12 +187,11 @@ bool gpu_takes(const uint8_t* hdr, int hlen) {
 }  // namespace
 
 void compressBlock(StringBuffer* in, Writer* out, const char* method, const char* filename, const char* comment, bool dosha1) {
-  // which methods the GPU core takes is decided by the library itself (zpq_model_from_method)
   uint8_t hdr[70000]; int hlen = 0;
-  const int probe = zpq_model_from_method(method, in->data(), in->size(), hdr, (int)sizeof(hdr), &hlen);
+  const int probe = probe_method(method, in->data(), in->size(), hdr, (int)sizeof(hdr), &hlen);
   if (probe == ZPQ_E_METHOD || probe == ZPQ_E_UNSUPPORTED || (probe == ZPQ_OK && hdr[6] == 0)) {
-    SHIM_LOG("compressBlock %d bytes method %s -> reference CPU code (not a context-model method)", (int)in->size(), method);
-    compressBlock_cpu(in, out, method, filename, comment, dosha1);     // LZ77 / BWT / stored: not on the hot path
+    SHIM_LOG("compressBlock %d bytes method %s -> reference CPU code (store / LZ77 selection)", (int)in->size(), method);
+    compressBlock_cpu(in, out, method, filename, comment, dosha1);     // LZ77 / stored: not on the hot path, no transform kernel for them
     return;
   }
   if (probe == ZPQ_OK && !gpu_takes(hdr, hlen))       // a modelled block the kernels cannot take: say so, never code it on the CPU
@@ -226,7 +240,7 @@ void compress(Reader* in, Writer* out, const char* method, const char* filename,
     std::vector<char> on_gpu(bufs.size(), 0);
     for (size_t i = 0; i < bufs.size(); ++i) {
       uint8_t hdr[70000]; int hlen = 0;
-      const int probe = zpq_model_from_method(method, bufs[i]->data(), bufs[i]->size(), hdr, (int)sizeof(hdr), &hlen);
+      const int probe = probe_method(method, bufs[i]->data(), bufs[i]->size(), hdr, (int)sizeof(hdr), &hlen);
       if (probe == ZPQ_OK && hdr[6] > 0 && !gpu_takes(hdr, hlen)) {
         for (size_t k = 0; k < i; ++k) if (on_gpu[k]) batcher().wait(&reqs[k]);
         for (StringBuffer* sb : bufs) delete sb;
