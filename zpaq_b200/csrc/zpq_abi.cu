@@ -667,14 +667,18 @@ int zpq_header_from_stats(const char* method, uint64_t n, const int32_t gaps[2],
 }
 
 // header + pre-processing kind + model prefix of a method (what compress_core builds per block)
-static int plan_block(const char* method, uint64_t n, const int g[2], std::vector<uint8_t>* hdr, int* prep, std::vector<uint8_t>* prefix, std::string* err) {
+static int plan_block(const char* method, uint64_t n, const int g[2], std::vector<uint8_t>* hdr, int* prep, std::vector<uint8_t>* prefix, std::string* err,
+                      int* size_class_out = nullptr, int* lz_out = nullptr) {
   int size_class = 0;
-  const int rc = block_plan(method, n, g, hdr, prep, &size_class, err);
+  int lz[5] = {0, 0, 0, 0, 0};
+  const int rc = block_plan(method, n, g, hdr, prep, &size_class, lz, err);
+  if (size_class_out) *size_class_out = size_class;
+  if (lz_out) for (int i = 0; i < 5; ++i) lz_out[i] = lz[i];
   if (rc != ZPQ_OK) return rc;
   prefix->assign(1, 0);                                  // PASS
   if (*prep != 0) {
     std::vector<uint8_t> code;
-    const int rp = pcomp_program(*prep, size_class, &code);
+    const int rp = pcomp_program(*prep, size_class, lz[0], &code);
     if (rp != ZPQ_OK) { *err = "no post-processor program for this pre-processing"; return rp; }
     pcomp_prefix(code, prefix);
   }
@@ -820,6 +824,12 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
     const int g2[2] = {gaps[2 * i], gaps[2 * i + 1]};
     st[i] = plan_block(method, len[i], g2, &hdrs[i], &prep[i], &prefix[i], &e);
     if (st[i] != ZPQ_OK) { if (ctx->err.empty() || st[i] == ZPQ_E_METHOD) ctx->err = e; continue; }
+    if ((prep[i] & 3) == 1 || (prep[i] & 3) == 2 || hdrs[i][6] == 0) {
+      // store / LZ77 selections: the plan (header, program) is known, the forward parser is not built (a sequential greedy
+      // parse with a hash table updated per byte, libzpaq.cpp:6660-6883): the caller keeps libzpaq's code for these
+      st[i] = ZPQ_E_METHOD; ctx->err = "store / LZ77 pre-processing is not built in this library";
+      continue;
+    }
     char cs[32];
     snprintf(cs, sizeof(cs), "%llu", (unsigned long long)len[i]);
     std::string comment = cs;                                   // libzpaq.cpp:7702-7703
@@ -1160,7 +1170,7 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
           const int ph = J.hdr[4], pm = J.hdr[5];
           if (ph != pm || ph < 20 || ph > 31 || J.seg_out.size() != 1) continue;
           std::vector<uint8_t> code, pre;
-          if (pcomp_program(3, ph - 20, &code) != ZPQ_OK) continue;
+          if (pcomp_program(3, ph - 20, 0, &code) != ZPQ_OK) continue;
           pcomp_prefix(code, &pre);
           if (J.out_len < pre.size() + 6 || memcmp(tmp[i].data(), pre.data(), pre.size()) != 0) continue;
           const uint64_t n = J.out_len - pre.size() - 5;

@@ -32,10 +32,11 @@ bool method_needs_gaps(const char* method);
 void payload_gaps(const uint8_t* data, uint64_t n, int gaps[2]);
 int header_from_stats(const char* method, uint64_t n, const int gaps[2], std::vector<uint8_t>* hdr, std::string* err);
 // header + the pre-processing the payload needs (0 none, 3 BWT, 4 E8E9, 7 E8E9 then BWT) + the block size class
-int block_plan(const char* method, uint64_t n, const int gaps[2], std::vector<uint8_t>* hdr, int* prep, int* size_class, std::string* err);
+// lz[5]: the LZ77 numbers of the method (minimum match, second order, log2 bucket, table bits, look-ahead) when prep is 1, 2, 5 or 6
+int block_plan(const char* method, uint64_t n, const int gaps[2], std::vector<uint8_t>* hdr, int* prep, int* size_class, int lz[5], std::string* err);
 
 // zpq_pcomp.cpp : the post-processor programs of transformed blocks (bytes identical to makeConfig + Compiler)
-int pcomp_program(int kind, int size_class, std::vector<uint8_t>* code);
+int pcomp_program(int kind, int size_class, int min_match, std::vector<uint8_t>* code);
 void pcomp_prefix(const std::vector<uint8_t>& code, std::vector<uint8_t>* prefix);
 
 // zpq_frame.cpp : SHA-1 and block framing

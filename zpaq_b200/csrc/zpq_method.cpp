@@ -86,9 +86,9 @@ std::vector<int> dominant_gaps(const uint8_t* p, unsigned n) {
 }
 
 // "LB[,R,T]": L = level digit, B = block size digits (ignored here: the block decides), R,T -> block type R*4+T
-// (bit 0 text, bit 1 exe; 512 when no type is given).  In scope: the context-mixing branches of levels 4 and 5 and the
-// BWT branches of levels 3 and 4, each with or without E8E9 (*prep = makeConfig's pre-processing number: 0, 3, 4, 7).
-int level_tokens(const std::string& m, uint64_t n64, const std::vector<int>& gaps, int* arg0, int* prep, std::vector<Token>* out, std::string* err) {
+// (bit 0 text, bit 1 exe; 512 when no type is given).  Every branch of libzpaq.cpp:7596-7650: store (an empty token list),
+// LZ77 (lz[] = its five numbers), BWT, context mixing, each with or without E8E9 (*prep = makeConfig's second number).
+int level_tokens(const std::string& m, uint64_t n64, const std::vector<int>& gaps, int* arg0, int* prep, int lz[5], std::vector<Token>* out, std::string* err) {
   const unsigned n = (unsigned)n64;
   *arg0 = std::max(bit_length(n + 4095) - 20, 0);
   int field[4] = {0, 0, 0, 0}, nsep = 0;
@@ -103,17 +103,48 @@ int level_tokens(const std::string& m, uint64_t n64, const std::vector<int>& gap
   std::vector<Token>& t = *out;
   t.clear();
   *prep = e8;
-  const char* kLz = "this block type selects store / LZ77 at this level: outside the context-mixing and BWT paths";
-  if (level <= 2) { *err = "levels 0-2 are store / LZ77 only: outside the context-mixing and BWT paths"; return ZPQ_E_METHOD; }
+  // LZ77 parameters (makeConfig's numbers 3..7: minimum match, second context order, log2 bucket, table bits, look-ahead);
+  // `tbl` = hash table bits for this block size, `sa` = "use the suffix array" (libzpaq.cpp:7586-7587)
+  const int tbl = 19 + *arg0 + (*arg0 <= 6 ? 1 : 0), sa = 21 + *arg0;
+  auto lz77 = [&](int kind, int a2, int a3, int a4, int a5, int a6) { *prep = kind + e8; lz[0] = a2; lz[1] = a3; lz[2] = a4; lz[3] = a5; lz[4] = a6; };
+  if (level == 0) { *prep = 0; return ZPQ_OK; }                      // "0B": stored, no model (an empty token list)
+  if (level == 1) {
+    if (type < 40) { *prep = 0; return ZPQ_OK; }                     // hard to compress: store
+    if (type < 80) lz77(1, 4, 0, 1, 15, 0);
+    else if (type < 128) lz77(1, 4, 0, 2, 16, 0);
+    else if (type < 256) lz77(1, 4, 0, 2, tbl, 0);
+    else if (type < 960) lz77(1, 5, 0, 3, tbl, 0);
+    else lz77(1, 6, 0, 3, tbl, 0);
+    return ZPQ_OK;
+  }
+  if (level == 2) {
+    if (type < 32) { *prep = 0; return ZPQ_OK; }
+    if (type < 64) lz77(1, 4, 0, 3, tbl, 0);
+    else lz77(1, 4, 0, 7, sa, 1);
+    return ZPQ_OK;
+  }
   if (level == 3) {
-    // BWT for text and for highly redundant blocks; everything else at this level is LZ77
-    if (type < 48 || !(type >= 640 || text)) { *err = kLz; return ZPQ_E_METHOD; }
-    *prep = 3 + e8;
-    t.push_back(tok('c')); t.push_back(tok('i', {1}));
+    if (type < 20) { *prep = 0; return ZPQ_OK; }
+    if (type < 48) { lz77(1, 4, 0, 3, tbl, 0); return ZPQ_OK; }
+    if (type >= 640 || text) {                                       // BWT for text and for highly redundant blocks
+      *prep = 3 + e8;
+      t.push_back(tok('c')); t.push_back(tok('i', {1}));
+      return ZPQ_OK;
+    }
+    lz77(2, 12, 0, 7, sa, 1);                                        // byte-aligned LZ77, orders 0-1 over literals and parse state
+    t.push_back(tok('c', {0, 0, 511})); t.push_back(tok('i', {2}));
     return ZPQ_OK;
   }
   if (level == 4) {
-    if (type < 48) { *err = kLz; return ZPQ_E_METHOD; }
+    if (type < 12) { *prep = 0; return ZPQ_OK; }
+    if (type < 24) { lz77(1, 4, 0, 3, tbl, 0); return ZPQ_OK; }
+    if (type < 48) {
+      // the reference glues "1c0,0,511" to the table-size number (libzpaq.cpp:7637): the sixth number becomes e.g. 211,
+      // which still means "suffix array", and there is no look-ahead number
+      lz77(2, 5, 0, 7, sa * 10 + 1, 0);
+      t.push_back(tok('c', {0, 0, 511}));
+      return ZPQ_OK;
+    }
     if (type >= 900) {
       *prep = 3 + e8;
       t.push_back(tok('c')); t.push_back(tok('i', {1}));
@@ -149,7 +180,7 @@ int level_tokens(const std::string& m, uint64_t n64, const std::vector<int>& gap
 // ---------------------------------------------------------------- 3. draft model and HCOMP assembly
 // ZPAQL opcodes used by the generator (indexes of the opcode list, libzpaq.cpp:2456-2491)
 enum {
-  A_INC = 1, A_ZERO = 4, A_R = 7, B_INC = 9, C_DEC = 18, D_INC = 25, PD_ZERO = 52, JT = 39, JF = 47, R_A = 55,
+  A_INC = 1, A_DEC = 2, A_ZERO = 4, A_R = 7, B_INC = 9, C_DEC = 18, D_INC = 25, PD_ZERO = 52, JT = 39, JF = 47, R_A = 55,
   HALT = 56, HASH = 59, HASHD = 60, JMP = 63,
   A_C = 66, A_PB = 68, A_PC = 69, A_PD = 70, A_N = 71, B_A = 72, B_C = 74, D_A = 88, D_N = 95,
   PC_A = 104, PD_A = 112, PD_C = 114,
@@ -206,6 +237,11 @@ struct Draft {
 
 // every program starts by pushing the new byte into the M ring and remembering where that byte value was last seen
 const Snip kProlog[] = {{C_DEC, NONE}, {PC_A, NONE}, {ADD_N, 255}, {D_A, NONE}, {PD_C, NONE}};
+// byte-aligned LZ77: R1 = 1 + bytes until the next code, R2 = first byte of the current code (libzpaq.cpp:7339-7357);
+// p0 = the length of the post-processor program that precedes the codes in the first segment
+const Snip kParseState[] = {{A_R, 1}, {EQ_N, 0}, {IF_, NONE}, {A_N, P(0)}, {ELSE_, NONE}, {EQ_N, 1}, {IF_, NONE}, {A_PC, NONE}, {R_A, 2},
+                            {GT_N, 63}, {IF_, NONE}, {SHR_N, 6}, {A_INC, NONE}, {A_INC, NONE}, {ELSE_, NONE}, {A_INC, NONE}, {A_INC, NONE}, {ENDIF_, NONE},
+                            {ELSE_, NONE}, {A_DEC, NONE}, {ENDIF_, NONE}, {ENDIF_, NONE}, {R_A, 1}};
 const Snip kClearH[] = {{D_N, P(0)}, {PD_ZERO, NONE}};                                   // H[p0] = 0
 const Snip kPosAnd[] = {{A_C, NONE}, {AND_N, P(0)}, {HASHD, NONE}};                      // position & (2^k - 1)
 const Snip kPosMod[] = {{A_C, NONE}, {MOD_N, P(0)}, {HASHD, NONE}};                      // position % period
@@ -385,7 +421,7 @@ int header_from_method(const char* method_, const uint8_t* data, uint64_t n, std
 
 // method (+ payload statistics) -> header bytes and the pre-processing the payload needs before it enters the model:
 // *prep = 0 none, 3 BWT, 4 E8E9, 7 E8E9 then BWT (makeConfig's second number, libzpaq.cpp:6894); LZ77 kinds are not built
-int block_plan(const char* method_, uint64_t n, const int gaps_in[2], std::vector<uint8_t>* hdr, int* prep, int* size_class_out, std::string* err) {
+int block_plan(const char* method_, uint64_t n, const int gaps_in[2], std::vector<uint8_t>* hdr, int* prep, int* size_class_out, int lz_out[5], std::string* err) {
   std::string e0;
   if (!err) err = &e0;
   if (!method_ || !method_[0]) { *err = "empty method"; return ZPQ_E_METHOD; }
@@ -393,10 +429,11 @@ int block_plan(const char* method_, uint64_t n, const int gaps_in[2], std::vecto
   const std::string ms = method_;
   std::vector<Token> tokens;
   int size_class = 0, preprocessing = 0;
+  int lz[5] = {0, 0, 0, 0, 0};
   if (isdigit((unsigned char)ms[0])) {
     std::vector<int> gaps;
     for (int i = 0; i < 2 && gaps_in && gaps_in[i] > 0; ++i) gaps.push_back(gaps_in[i]);
-    const int rc = level_tokens(ms, n, gaps, &size_class, &preprocessing, &tokens, err);
+    const int rc = level_tokens(ms, n, gaps, &size_class, &preprocessing, lz, &tokens, err);
     if (rc != ZPQ_OK) return rc;
   }
   else if (ms[0] == 'x') {
@@ -409,12 +446,23 @@ int block_plan(const char* method_, uint64_t n, const int gaps_in[2], std::vecto
       else if (++k < 9) head[k] = 0;
     }
     size_class = head[0]; preprocessing = head[1];
+    for (int i = 0; i < 5; ++i) lz[i] = head[2 + i];
     tokens = tokenize(s);
   }
   else { *err = "Unsupported method"; return ZPQ_E_METHOD; }
-  if (preprocessing != 0 && preprocessing != 3 && preprocessing != 4 && preprocessing != 7) {
-    *err = "LZ77 pre-processing is outside the context-mixing and BWT paths"; return ZPQ_E_METHOD;
+  if (isdigit((unsigned char)ms[0]) && ms[0] == '0') {
+    // level 0: "comp 0 0 0 0 0 hcomp end" -- no machines, no components, no program (libzpaq.cpp:6914-6916)
+    static const uint8_t kNone[9] = {7, 0, 0, 0, 0, 0, 0, 0, 0};
+    hdr->assign(kNone, kNone + 9);
+    if (prep) *prep = 0;
+    if (size_class_out) *size_class_out = size_class;
+    if (lz_out) for (int i = 0; i < 5; ++i) lz_out[i] = 0;
+    return ZPQ_OK;
   }
+  if (preprocessing < 0 || preprocessing > 7) { *err = "Unsupported method"; return ZPQ_E_METHOD; }
+  const int lzkind = preprocessing & 3;
+  if ((lzkind == 1 && lz[0] < 4) || (lzkind == 2 && lz[0] < 1)) { *err = "match length $3 too small"; return ZPQ_E_METHOD; }
+  if ((lzkind == 1 || lzkind == 2) && (lz[0] > 255 || lz[2] > 16 || lz[3] < 1 || lz[3] > 1000)) { *err = "LZ77 arguments out of range"; return ZPQ_E_METHOD; }
   if (size_class > 11) { *err = "block size argument too big"; return ZPQ_E_METHOD; }
   // the inverse BWT keeps the block (n + 5 bytes) in a 2^(20 + size class) byte array
   if ((preprocessing & 3) == 3 && n + 4096 > ((uint64_t)0x100000 << size_class)) { *err = "block does not fit the method's block size"; return ZPQ_E_METHOD; }
@@ -422,16 +470,19 @@ int block_plan(const char* method_, uint64_t n, const int gaps_in[2], std::vecto
   Draft d;
   d.membits = size_class + 20;
   d.emit(kProlog);
+  if (lzkind == 2) d.emit(kParseState, {111 + (preprocessing >= 4 ? 57 : 0)});
   for (const Token& t : tokens) {
     if (d.count() >= 254) break;
     for (const Family& f : kFamilies) if (f.letter == t.letter) { f.build(d, t); break; }
   }
   one(d, HALT);
   if (!d.ok || !d.open_jumps.empty() || d.count() > 255) { *err = "method arguments out of range"; return ZPQ_E_METHOD; }
-  const bool bwt = (preprocessing & 3) == 3;
+  const bool bwt = lzkind == 3;
   if (prep) *prep = preprocessing;
   if (size_class_out) *size_class_out = size_class;
-  return serialise(d, bwt ? size_class + 20 : 0, bwt ? size_class + 20 : 0, hdr, err);
+  if (lz_out) for (int i = 0; i < 5; ++i) lz_out[i] = lz[i];
+  // the post-processor's machine: BWT keeps list and bytes (H and M of 2^(20 + size class)), LZ77 only the bytes (libzpaq.cpp:6923, 7076, 7137)
+  return serialise(d, bwt ? size_class + 20 : 0, (bwt || lzkind == 1 || lzkind == 2) ? size_class + 20 : 0, hdr, err);
 }
 
 // header only, for callers that feed the model themselves (zpq_model_from_method, zpq_header_from_stats): a method that
@@ -440,9 +491,11 @@ int header_from_stats(const char* method_, uint64_t n, const int gaps_in[2], std
   std::string e0;
   if (!err) err = &e0;
   int prep = 0;
-  const int rc = block_plan(method_, n, gaps_in, hdr, &prep, nullptr, err);
+  const int rc = block_plan(method_, n, gaps_in, hdr, &prep, nullptr, nullptr, err);
   if (rc != ZPQ_OK) return rc;
-  if (prep != 0) { hdr->clear(); *err = "this method pre-processes the payload (E8E9 / BWT): use zpq_compress_blocks"; return ZPQ_E_METHOD; }
+  if (prep != 0 || (hdr->size() > 6 && (*hdr)[6] == 0)) {
+    hdr->clear(); *err = "this method stores or pre-processes the payload (E8E9 / BWT / LZ77): use zpq_compress_blocks"; return ZPQ_E_METHOD;
+  }
   return ZPQ_OK;
 }
 

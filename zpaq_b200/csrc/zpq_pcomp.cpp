@@ -90,8 +90,10 @@ struct PAsm {
 void pull_byte(PAsm& p) { p.o(dec(rB)).o(alu(SHL, IMM), 8).o(alu(ADD, pB)); }
 
 // un-rewrite E8 / E9 operands in M[0..d) and write M out (second pass of the BWT + E8E9 blocks up to 16 MiB, and of LZ77 + E8E9)
-void e8e9_pass_over_m(PAsm& p) {
-  p.o(set(rD, rB)).o(zero(rB)).Do();
+void e8e9_pass_over_m(PAsm& p, bool end_in_r4 = false) {
+  if (end_in_r4) p.o(zero(rB)).o(load_r(rD), 4);
+  else p.o(set(rD, rB)).o(zero(rB));
+  p.Do();
   p.o(set(rA, rB)).o(alu(EQ, rD)).IfNot();
   p.o(alu(ADD, IMM), 4).o(alu(LT, rD)).If();
   p.o(set(rA, pB)).o(alu(AND, IMM), 254).o(alu(EQ, IMM), 232).If();
@@ -201,6 +203,146 @@ std::vector<uint8_t> bwt_program(bool e8, bool upto16m, bool* ok) {
   return p.code;
 }
 
+// "a = bits" then shift `k` bits out of the bit buffer c
+void drop_bits(PAsm& p, int k) { p.o(set(rA, rC)).o(alu(SHR, IMM), k).o(set(rC, rA)); }
+
+// LZ77 with variable-length codes (LZBuffer level 1).  R1 = state, R2 = length being read, R3 = offset bits to come,
+// R4 = write pointer into M, R5 = low offset bits (blocks above 16 MiB: rb of them), c = bit buffer, d = bits in it.
+// States: 0 new code, 1 match length, 5 low offset bits, 2 offset, 3 literal length, 4 literals.
+std::vector<uint8_t> lz77_bits_program(bool e8, int rb, bool* ok) {
+  PAsm p;
+  p.o(alu(GT, IMM), 255).If();
+  if (e8) e8e9_pass_over_m(p, true);
+  p.o(zero(rA)).o(zero(rB)).o(zero(rC)).o(zero(rD)).o(STORE_R, 1).o(STORE_R, 2).o(STORE_R, 3).o(STORE_R, 4);
+  p.o(HALT);
+  p.EndIf();
+  // the new byte on top of the bit buffer
+  p.o(alu(SHL, rD)).o(alu(ADD, rC)).o(set(rC, rA));
+  p.o(set(rA, IMM), 8).o(alu(ADD, rD)).o(set(rD, rA));
+  // state 0: two bits say literal run (00) or match (offset width class), three more the width inside the class
+  p.o(load_r(rA), 1).o(alu(EQ, IMM), 0).If();
+  p.o(set(rA, IMM), 1).o(STORE_R, 2);
+  p.o(set(rA, rC)).o(alu(AND, IMM), 3).o(alu(GT, IMM), 0).If();
+  p.o(dec(rA)).o(alu(SHL, IMM), 3).o(STORE_R, 3);
+  drop_bits(p, 2);
+  p.o(load_r(rB), 3).o(alu(AND, IMM), 7).o(alu(ADD, rB)).o(STORE_R, 3);
+  drop_bits(p, 3);
+  p.o(set(rA, rD)).o(alu(SUB, IMM), 5).o(set(rD, rA));
+  p.o(set(rA, IMM), 1).o(STORE_R, 1);
+  p.Else();
+  drop_bits(p, 2);
+  p.o(dec(rD)).o(dec(rD));
+  p.o(set(rA, IMM), 3).o(STORE_R, 1);
+  p.EndIf();
+  p.EndIf();
+  // state 1: interleaved Elias-gamma length, then its two low bits
+  p.Do().o(load_r(rA), 1).o(alu(EQ, IMM), 1).If().o(set(rA, rD)).o(alu(GT, IMM), 2).If();
+  p.o(set(rA, rC)).o(alu(AND, IMM), 1).o(alu(EQ, IMM), 1).If();
+  drop_bits(p, 1);
+  p.o(load_r(rB), 2).o(set(rA, rC)).o(alu(AND, IMM), 1).o(alu(ADD, rB)).o(alu(ADD, rB)).o(STORE_R, 2);
+  drop_bits(p, 1);
+  p.o(dec(rD)).o(dec(rD));
+  p.Else();
+  drop_bits(p, 1);
+  p.o(load_r(rA), 2).o(alu(SHL, IMM), 2).o(set(rB, rA));
+  p.o(set(rA, rC)).o(alu(AND, IMM), 3).o(alu(ADD, rB)).o(STORE_R, 2);
+  drop_bits(p, 2);
+  p.o(dec(rD)).o(dec(rD)).o(dec(rD));
+  p.o(set(rA, IMM), rb ? 5 : 2).o(STORE_R, 1);
+  p.EndIf();
+  p.Forever().EndIf().EndIf();
+  if (rb) {
+    p.o(load_r(rA), 1).o(alu(EQ, IMM), 5).If().o(set(rA, rD)).o(alu(GT, IMM), rb - 1).If();
+    p.o(set(rA, rC)).o(alu(AND, IMM), (1 << rb) - 1).o(STORE_R, 5);
+    drop_bits(p, rb);
+    p.o(set(rA, rD)).o(alu(SUB, IMM), rb).o(set(rD, rA));
+    p.o(set(rA, IMM), 2).o(STORE_R, 1);
+    p.EndIf().EndIf();
+  }
+  // state 2: the offset, then the copy
+  p.o(load_r(rA), 1).o(alu(EQ, IMM), 2).If().o(load_r(rA), 3).o(alu(GT, rD)).IfNot();
+  p.o(set(rA, rC)).o(STORE_R, 6).o(set(rA, rD)).o(STORE_R, 7);
+  p.o(load_r(rB), 3).o(set(rA, IMM), 1).o(alu(SHL, rB)).o(set(rD, rA));
+  p.o(dec(rA)).o(alu(AND, rC)).o(alu(ADD, rD));
+  if (rb) p.o(alu(SHL, IMM), rb).o(load_r(rD), 5).o(alu(ADD, rD)).o(alu(SUB, IMM), (1 << rb) - 1);
+  p.o(set(rD, rA)).o(load_r(rB), 4).o(set(rA, rB)).o(alu(SUB, rD)).o(set(rC, rA));
+  p.o(load_r(rD), 2).Do().o(set(rA, rD)).o(alu(GT, IMM), 0).If().o(dec(rD));
+  p.o(set(rA, pC)).o(set(pB, rA)).o(inc(rC)).o(inc(rB));
+  if (!e8) p.o(OUT);
+  p.Forever().EndIf();
+  p.o(set(rA, rB)).o(STORE_R, 4);
+  p.o(load_r(rA), 6).o(load_r(rB), 3).o(alu(SHR, rB)).o(set(rC, rA));
+  p.o(load_r(rA), 7).o(alu(SUB, rB)).o(set(rD, rA));
+  p.o(zero(rA)).o(STORE_R, 1);
+  p.EndIf().EndIf();
+  // state 3: literal run length
+  p.Do().o(load_r(rA), 1).o(alu(EQ, IMM), 3).If().o(set(rA, rD)).o(alu(GT, IMM), 1).If();
+  p.o(set(rA, rC)).o(alu(AND, IMM), 1).o(alu(EQ, IMM), 1).If();
+  drop_bits(p, 1);
+  p.o(load_r(rB), 2).o(alu(AND, IMM), 1).o(alu(ADD, rB)).o(alu(ADD, rB)).o(STORE_R, 2);
+  drop_bits(p, 1);
+  p.o(dec(rD)).o(dec(rD));
+  p.Else();
+  drop_bits(p, 1);
+  p.o(dec(rD));
+  p.o(set(rA, IMM), 4).o(STORE_R, 1);
+  p.EndIf();
+  p.Forever().EndIf().EndIf();
+  // state 4: one literal
+  p.o(load_r(rA), 1).o(alu(EQ, IMM), 4).If().o(set(rA, rD)).o(alu(GT, IMM), 7).If();
+  p.o(load_r(rB), 4).o(set(rA, rC)).o(set(pB, rA));
+  if (!e8) p.o(OUT);
+  p.o(inc(rB)).o(set(rA, rB)).o(STORE_R, 4);
+  drop_bits(p, 8);
+  p.o(set(rA, rD)).o(alu(SUB, IMM), 8).o(set(rD, rA));
+  p.o(load_r(rA), 2).o(dec(rA)).o(STORE_R, 2).o(alu(EQ, IMM), 0).If();
+  p.o(zero(rA)).o(STORE_R, 1);
+  p.EndIf();
+  p.EndIf().EndIf();
+  p.o(HALT);
+  *ok = p.ok && p.ifs.empty() && p.dos.empty();
+  return p.code;
+}
+
+// Byte-aligned LZ77 (LZBuffer level 2).  d = state (0 new code, 1 literals, 2 last offset byte, 3.. offset bytes to come),
+// R1 = length, R2 = offset so far, M = output, b = write pointer.
+std::vector<uint8_t> lz77_bytes_program(bool e8, int min_match, bool* ok) {
+  PAsm p;
+  p.o(alu(GT, IMM), 255).If();
+  if (e8) e8e9_pass_over_m(p);
+  p.o(zero(rB)).o(zero(rC)).o(zero(rD)).o(zero(rA)).o(STORE_R, 1).o(STORE_R, 2);
+  p.o(HALT);
+  p.EndIf();
+  p.o(set(rC, rA)).o(set(rA, rD)).o(alu(EQ, IMM), 0).If();
+  p.o(set(rA, rC)).o(alu(SHR, IMM), 6).o(inc(rA)).o(set(rD, rA));
+  p.o(alu(EQ, IMM), 1).If();
+  p.o(alu(ADD, rC)).o(STORE_R, 1).o(zero(rA)).o(STORE_R, 2);
+  p.Else();
+  p.o(inc(rD)).o(set(rA, rC)).o(alu(AND, IMM), 63).o(alu(ADD, IMM), min_match).o(STORE_R, 1).o(zero(rA)).o(STORE_R, 2);
+  p.EndIf();
+  p.Else();
+  p.o(alu(EQ, IMM), 1).If();
+  p.o(set(rA, rC)).o(set(pB, rA)).o(inc(rB));
+  if (!e8) p.o(OUT);
+  p.o(load_r(rA), 1).o(dec(rA)).o(alu(EQ, IMM), 0).If().o(zero(rD)).EndIf().o(STORE_R, 1);
+  p.Else();
+  p.o(alu(GT, IMM), 2).If();
+  p.o(load_r(rA), 2).o(alu(SHL, IMM), 8).o(alu(OR, rC)).o(STORE_R, 2).o(dec(rD));
+  p.Else();
+  p.o(load_r(rA), 2).o(alu(SHL, IMM), 8).o(alu(OR, rC)).o(set(rC, rA)).o(set(rA, rB)).o(alu(SUB, rC)).o(dec(rA)).o(set(rC, rA));
+  p.o(load_r(rD), 1);
+  p.Do();
+  p.o(set(rA, pC)).o(set(pB, rA)).o(inc(rC)).o(inc(rB));
+  if (!e8) p.o(OUT);
+  p.o(dec(rD)).o(set(rA, rD)).o(alu(GT, IMM), 0).While();
+  p.EndIf();
+  p.EndIf();
+  p.EndIf();
+  p.o(HALT);
+  *ok = p.ok && p.ifs.empty() && p.dos.empty();
+  return p.code;
+}
+
 std::vector<uint8_t> e8e9_program(bool* ok) {
   PAsm p;
   p.o(alu(GT, IMM), 255).If();
@@ -234,12 +376,14 @@ std::vector<uint8_t> e8e9_program(bool* ok) {
 
 }  // namespace
 
-// kind = makeConfig's second number: 3 BWT, 4 E8E9 only, 7 E8E9 + BWT.  Returns the program bytes WITHOUT the closing
-// END byte (the prefix adds it), empty on an unsupported kind.
-int pcomp_program(int kind, int size_class, std::vector<uint8_t>* code) {
+// kind = makeConfig's second number: 1 LZ77 with variable-length codes, 2 byte-aligned LZ77 (min_match = its third number),
+// 3 BWT, 4 E8E9 only, 5 / 6 / 7 = E8E9 + 1 / 2 / 3.  Returns the program bytes WITHOUT the closing END byte (the prefix adds it).
+int pcomp_program(int kind, int size_class, int min_match, std::vector<uint8_t>* code) {
   bool ok = false;
   if (kind == 4) *code = e8e9_program(&ok);
   else if (kind == 3 || kind == 7) *code = bwt_program(kind == 7, size_class <= 4, &ok);
+  else if (kind == 1 || kind == 5) *code = lz77_bits_program(kind == 5, size_class > 4 ? size_class - 4 : 0, &ok);
+  else if (kind == 2 || kind == 6) *code = lz77_bytes_program(kind == 6, min_match, &ok);
   else return ZPQ_E_METHOD;
   return ok ? ZPQ_OK : ZPQ_E_METHOD;
 }
