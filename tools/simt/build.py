@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "zpaq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
-CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_kernels8.cu", "zpq_prep.cu", "zpq_bwt.cu", "zpq_abi.cu"]
+CU = ["zpq_kernels.cu", "zpq_kernels2.cu", "zpq_kernels5.cu", "zpq_kernels6.cu", "zpq_kernels7.cu", "zpq_kernels8.cu", "zpq_prep.cu", "zpq_bwt.cu", "zpq_lz77.cu", "zpq_abi.cu"]
 CPP = ["zpq_model.cpp", "zpq_method.cpp", "zpq_pcomp.cpp", "zpq_frame.cpp", "zpq_hcomp.cpp"]
 
 

@@ -13,6 +13,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <array>
 #include "zpq_host.h"
 #include "zpq_kernels.h"
 
@@ -68,7 +69,7 @@ struct zpq_ctx {
   float ms_prep = 0;           // device time of the last analysis pass (SHA-1, gap statistics); added to ms[0] by the whole-block calls
   uint64_t xform_bytes = 0;    // algorithmic HBM bytes of the last pre-processing pass (zpq_bwt_forward)
   float ms_xform = 0;          // device time of the last pre-processing pass (E8E9, BWT: zpq_bwt.cu); added to ms[0] as well
-  DevBuf d_xform, d_xws;       // transformed payloads; workspace of the suffix sorter
+  DevBuf d_xform, d_xws, d_lz; // transformed payloads; workspace of the suffix sorter; LZ77 tables
   uint64_t launches = 0;
   uint32_t tiers[7] = {0, 0, 0, 0, 0, 0, 0};   // blocks of the last batch per kernel tier (zpq_last_tiers)
   int wave_group = 16;         // blocks per component warp of the wavefront encoder (ZPQ_GROUP overrides)
@@ -590,7 +591,7 @@ void zpq_destroy(zpq_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release(); ctx->d_prep.release(); ctx->d_xform.release(); ctx->d_xws.release(); ctx->d_stage_in.release(); ctx->d_stage_out.release(); for (int i = 0; i < 4; ++i) ctx->d_groups[i].release();
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_meta.release(); ctx->d_pbuf.release(); ctx->d_cstate.release(); ctx->d_prep.release(); ctx->d_xform.release(); ctx->d_xws.release(); ctx->d_lz.release(); ctx->d_stage_in.release(); ctx->d_stage_out.release(); for (int i = 0; i < 4; ++i) ctx->d_groups[i].release();
   if (ctx->own_ws && ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -818,16 +819,19 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
   // ---- host: header bytes, pre-processing kind, model prefix and block prologue from (method, length, gaps) ----
   std::vector<std::vector<uint8_t>> hdrs(nblk), pro(nblk), prefix(nblk);
   std::vector<int> prep(nblk, 0);
+  std::vector<std::array<int, 7>> lzn(nblk);      // makeConfig's $1..$7 of every block (LZ77 parameters)
   for (int i = 0; i < nblk; ++i) {
     if (st[i] != ZPQ_OK) continue;
     std::string e;
     const int g2[2] = {gaps[2 * i], gaps[2 * i + 1]};
-    st[i] = plan_block(method, len[i], g2, &hdrs[i], &prep[i], &prefix[i], &e);
+    int sc = 0, lz5[5] = {0, 0, 0, 0, 0};
+    st[i] = plan_block(method, len[i], g2, &hdrs[i], &prep[i], &prefix[i], &e, &sc, lz5);
     if (st[i] != ZPQ_OK) { if (ctx->err.empty() || st[i] == ZPQ_E_METHOD) ctx->err = e; continue; }
-    if ((prep[i] & 3) == 1 || (prep[i] & 3) == 2 || hdrs[i][6] == 0) {
-      // store / LZ77 selections: the plan (header, program) is known, the forward parser is not built (a sequential greedy
-      // parse with a hash table updated per byte, libzpaq.cpp:6660-6883): the caller keeps libzpaq's code for these
-      st[i] = ZPQ_E_METHOD; ctx->err = "store / LZ77 pre-processing is not built in this library";
+    lzn[i] = {sc, prep[i], lz5[0], lz5[1], lz5[2], lz5[3], lz5[4]};
+    if (((prep[i] & 3) == 1 || (prep[i] & 3) == 2) && lz5[1] != 0) {
+      // LZ77 with a second, longer context order probes bytes past the end of the block in the reference
+      // (libzpaq.cpp:6700, no bound on in[i+3]): not reproducible, and no digit method selects it
+      st[i] = ZPQ_E_METHOD; ctx->err = "LZ77 with a second context order ($4 > 0) is not built";
       continue;
     }
     char cs[32];
@@ -844,13 +848,14 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
   ctx->ms_xform = 0; ctx->xform_bytes = 0;
   {
     uint64_t tot = 0;
-    std::vector<uint64_t> off_e8(nblk, 0), off_bwt(nblk, 0);
+    std::vector<uint64_t> off_e8(nblk, 0), off_bwt(nblk, 0), off_lz(nblk, 0);
     bool any = false;
     for (int i = 0; i < nblk; ++i) {
       if (st[i] != ZPQ_OK || prep[i] == 0) continue;
       any = true;
       if (prep[i] & 4) { off_e8[i] = tot; tot = align_up(tot + len[i] + 16, 256); }
       if ((prep[i] & 3) == 3) { off_bwt[i] = tot; tot = align_up(tot + len[i] + 5 + 16, 256); }
+      if ((prep[i] & 3) == 1 || (prep[i] & 3) == 2) { off_lz[i] = tot; tot = align_up(tot + len[i] + len[i] / 8 + 1024 + 16, 256); }
     }
     if (any) {
       CK(ctx->d_xform.reserve(tot + 256), "pre-processing cudaMalloc");
@@ -897,6 +902,56 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
           k = e;
         }
       }
+      // LZ77 (LZBuffer levels 1 / 2): one thread per block (zpq_lz77.cu); blocks with the same numbers go together, the
+      // suffix-array variant sorts its sub-batch with the BWT's sorter first
+      {
+        std::vector<char> done(nblk, 0);
+        for (int i0 = 0; i0 < nblk; ++i0) {
+          if (done[i0] || st[i0] != ZPQ_OK || ((prep[i0] & 3) != 1 && (prep[i0] & 3) != 2)) continue;
+          std::vector<int> ids;
+          for (int i = i0; i < nblk; ++i)
+            if (!done[i] && st[i] == ZPQ_OK && lzn[i] == lzn[i0]) { ids.push_back(i); done[i] = 1; }
+          const int* numbers = lzn[i0].data();
+          const bool use_sa = zpq_lz77_uses_sa(numbers) != 0;
+          const uint64_t tb = zpq_lz77_table_bytes(numbers);
+          size_t k = 0;
+          while (k < ids.size()) {
+            uint64_t sum = 0; size_t e = k;
+            while (e < ids.size() && e - k < 60000 && (e == k || (sum + len[ids[e]] <= ((uint64_t)1 << 28) && (e - k + 1) * tb <= ((uint64_t)8 << 30)))) sum += len[ids[e++]];
+            const int cnt = (int)(e - k);
+            std::vector<const uint8_t*> lin; std::vector<uint8_t*> lout; std::vector<uint64_t> llen, lcap, olen(cnt, 0); std::vector<int> lst(cnt, 0);
+            for (size_t j = k; j < e; ++j) {
+              const int i = ids[j];
+              lin.push_back(d_model_in[i]); lout.push_back(dx + off_lz[i]); llen.push_back(len[i]); lcap.push_back(len[i] + len[i] / 8 + 1024);
+            }
+            const uint32_t *d_sa = nullptr, *d_rank = nullptr, *d_off = nullptr;
+            std::vector<uint32_t> base(cnt, 0);
+            bool ok = ctx->d_lz.reserve(tb * (uint64_t)cnt + zpq_lz77_meta_bytes(cnt)) == cudaSuccess;
+            if (ok && use_sa) {
+              ok = ctx->d_xws.reserve(zpq_bwt_workspace(sum, cnt)) == cudaSuccess;
+              if (ok) {
+                CK(zpq_suffix_arrays(lin.data(), llen.data(), cnt, ctx->d_xws.p, ctx->d_xws.cap, ctx->sm_count, stream, &ctx->launches, &ctx->xform_bytes,
+                                     &d_sa, &d_rank, &d_off), "suffix sort kernels");
+                for (int j = 1; j < cnt; ++j) base[j] = base[j - 1] + (uint32_t)llen[j - 1];
+              }
+            }
+            if (!ok) {
+              cudaGetLastError();
+              for (size_t j = k; j < e; ++j) st[ids[j]] = ZPQ_E_NOMEM;
+              ctx->err = "Out of memory";
+            } else {
+              CK(zpq_lz77_forward(lin.data(), llen.data(), lout.data(), lcap.data(), cnt, numbers, ctx->d_lz.p, d_sa, d_rank, base.data(),
+                                  (uint8_t*)ctx->d_lz.p + tb * (uint64_t)cnt, olen.data(), lst.data(), stream, &ctx->launches), "zpq_lz77_kernel launch");
+              for (size_t j = k; j < e; ++j) {
+                const int i = ids[j];
+                if (lst[j - k]) { st[i] = ZPQ_E_NOMEM; continue; }
+                d_model_in[i] = dx + off_lz[i]; model_len[i] = olen[j - k];
+              }
+            }
+            k = e;
+          }
+        }
+      }
       CK(cudaEventRecord(ctx->ev[1], stream), "event");
       CK(cudaStreamSynchronize(stream), "pre-processing");
       float ms = 0;
@@ -917,9 +972,36 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
   // ---- the coding path ----
   std::vector<IJob> jobs;
   std::vector<int> idx;
+  std::vector<uint64_t> stored_len(nblk, 0);          // body length of blocks without a model (stored in 64 KiB chunks)
+  std::vector<uint8_t> spool; std::vector<uint64_t> s_src; std::vector<uint8_t*> s_dst; std::vector<uint32_t> s_nb;
   for (int i = 0; i < nblk; ++i) {
     if (st[i] != ZPQ_OK) continue;
     const uint64_t tail = 4 + (dosha1 ? 21 : 1) + 1;
+    if (hdrs[i][6] == 0) {
+      // no components: Encoder::compress without a model (libzpaq.cpp:2436-2445) -- the bytes that would go through the model
+      // (prefix, then the possibly transformed payload) leave in chunks of 64 KiB, each behind its length (4 bytes, MSB first)
+      const uint64_t P = prefix[i].size(), L = P + model_len[i];
+      const uint64_t body = L + 4 * ((L + 65535) / 65536);
+      if (out_cap[i] < pro[i].size() + body + tail) { st[i] = ZPQ_E_OUTPUT_FULL; continue; }
+      uint8_t* dst = d_out[i] + pro[i].size();
+      for (uint64_t at = 0; at < L; at += 65536) {
+        const uint64_t cl = std::min<uint64_t>(65536, L - at);
+        const size_t h0 = spool.size();
+        spool.push_back((uint8_t)(cl >> 24)); spool.push_back((uint8_t)(cl >> 16)); spool.push_back((uint8_t)(cl >> 8)); spool.push_back((uint8_t)cl);
+        uint64_t from_prefix = at < P ? std::min<uint64_t>(cl, P - at) : 0;
+        spool.insert(spool.end(), prefix[i].begin() + (at < P ? at : P), prefix[i].begin() + (at < P ? at : P) + from_prefix);
+        s_src.push_back(h0); s_dst.push_back(dst); s_nb.push_back((uint32_t)(4 + from_prefix));
+        dst += 4 + from_prefix;
+        const uint64_t from_data = cl - from_prefix;
+        if (from_data) {
+          const uint64_t doff = at + from_prefix - P;
+          CK(cudaMemcpyAsync(dst, d_model_in[i] + doff, from_data, cudaMemcpyDeviceToDevice, stream), "stored chunk");
+          dst += from_data;
+        }
+      }
+      stored_len[i] = body;
+      continue;
+    }
     IJob J;
     J.hdr = hdrs[i].data(); J.hlen = (int)hdrs[i].size();
     J.in.push_back(Piece{prefix[i].data(), prefix[i].size()});      // PASS byte, or "1, len, PCOMP program" (libzpaq.cpp:2905-2915)
@@ -934,20 +1016,30 @@ static int compress_core(zpq_ctx* ctx, int nblk, const char* method, const uint8
   // ---- framing around the coded data (Compressor::endSegment / endBlock, libzpaq.cpp:2956-3002), written on the device ----
   {
     std::vector<uint8_t> pool; std::vector<uint64_t> src_off; std::vector<uint8_t*> dst; std::vector<uint32_t> nb;
+    std::vector<uint64_t> body_len(nblk, 0); std::vector<char> have(nblk, 0);
     for (size_t k = 0; k < jobs.size(); ++k) {
       const int i = idx[k];
       st[i] = jobs[k].status;
-      if (st[i] != ZPQ_OK) continue;
+      if (st[i] == ZPQ_OK) { body_len[i] = jobs[k].out_len; have[i] = 1; }
+    }
+    for (int i = 0; i < nblk; ++i) if (st[i] == ZPQ_OK && hdrs[i].size() > 6 && hdrs[i][6] == 0) { body_len[i] = stored_len[i]; have[i] = 1; }
+    // chunk headers (and program bytes) of the stored blocks share the framing pool
+    for (size_t r = 0; r < s_src.size(); ++r) { src_off.push_back(pool.size() + s_src[r]); dst.push_back(s_dst[r]); nb.push_back(s_nb[r]); }
+    pool.insert(pool.end(), spool.begin(), spool.end());
+    for (int i = 0; i < nblk; ++i) {
+      if (!have[i] || st[i] != ZPQ_OK) continue;
+      struct { uint64_t out_len; } jk = {body_len[i]};
+      const auto* jobs_k = &jk;
       src_off.push_back(pool.size()); dst.push_back(d_out[i]); nb.push_back((uint32_t)pro[i].size());
       pool.insert(pool.end(), pro[i].begin(), pro[i].end());
-      src_off.push_back(pool.size()); dst.push_back(d_out[i] + pro[i].size() + jobs[k].out_len);
+      src_off.push_back(pool.size()); dst.push_back(d_out[i] + pro[i].size() + jobs_k->out_len);
       const size_t t0 = pool.size();
       pool.insert(pool.end(), 4, 0);
       if (dosha1) { pool.push_back(253); pool.insert(pool.end(), sha.begin() + (size_t)i * 20, sha.begin() + (size_t)i * 20 + 20); }
       else pool.push_back(254);
       pool.push_back(255);
       nb.push_back((uint32_t)(pool.size() - t0));
-      out_len[i] = pro[i].size() + jobs[k].out_len + (pool.size() - t0);
+      out_len[i] = pro[i].size() + jobs_k->out_len + (pool.size() - t0);
     }
     const int nrec = (int)dst.size();
     if (nrec) {

@@ -385,12 +385,14 @@ extern "C" uint64_t zpq_bwt_workspace(uint64_t total, int nb) {
   return w;
 }
 
-// in[b] / out[b]: DEVICE pointers (host arrays of them); len[b] host.  out[b] receives len[b] + 5 bytes.
+namespace {
+struct SortView { const u8* txt; const u32* sa; const u32* rank_of; const u32* d_off; BwtBlocks B; u32 n; int maxg; };
+
+// suffix arrays of all blocks in one index space (see the header): `out` may be null (no BWT emitted by the caller).
 // alg_bytes (optional): algorithmic HBM bytes of the kernels launched, for the roofline: per sort pass 8 (histogram read) +
 // 12 + 12 (scatter read + write) per active suffix, per round 100 more (keys, heads, two scans, update, compaction).
-extern "C" cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, int nb,
-                                       void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches, uint64_t* alg_bytes) {
-  if (nb <= 0) return cudaSuccess;
+cudaError_t suffix_sort_core(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, int nb,
+                             void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches, uint64_t* alg_bytes, SortView* V) {
   if (nb > 65535) return cudaErrorInvalidValue;
   u64 total = 0;
   for (int b = 0; b < nb; ++b) total += len[b];
@@ -422,7 +424,7 @@ extern "C" cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t*
   cudaError_t e;
   if ((e = cudaMemcpyAsync(d_off, h_off, (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) { delete[] h_off; return e; }
   if ((e = cudaMemcpyAsync(d_in, in, (size_t)nb * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) { delete[] h_off; return e; }
-  if ((e = cudaMemcpyAsync(d_out, out, (size_t)nb * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) { delete[] h_off; return e; }
+  if (out && (e = cudaMemcpyAsync(d_out, out, (size_t)nb * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) { delete[] h_off; return e; }
   e = cudaStreamSynchronize(st);
   delete[] h_off;
   if (e != cudaSuccess) return e;
@@ -469,18 +471,43 @@ extern "C" cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t*
     }
     m = m_next;
   }
-  {
-    u32 maxlen = 0;
-    for (int b = 0; b < nb; ++b) maxlen = len[b] > maxlen ? (u32)len[b] : maxlen;
-    dim3 g((unsigned)grid(maxlen + 1), (unsigned)nb);
-    if (g.x * (unsigned)nb > (unsigned)maxg * 4u) g.x = ((unsigned)maxg * 4u + nb - 1) / nb;
-    if (g.x == 0) g.x = 1;
-    zpq_bwt_emit<<<g, 256, 0, st>>>(B, txt, sa); ++nl;
-    ab += (u64)n * 6;
-  }
+  V->txt = txt; V->sa = sa; V->rank_of = rank_of; V->d_off = d_off; V->B = B; V->n = n; V->maxg = maxg;
   if (launches) *launches += nl;
   if (alg_bytes) *alg_bytes += ab;
   return cudaGetLastError();
+}
+}  // namespace
+
+// in[b] / out[b]: DEVICE pointers (host arrays of them); len[b] host.  out[b] receives len[b] + 5 bytes.
+extern "C" cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, int nb,
+                                       void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches, uint64_t* alg_bytes) {
+  if (nb <= 0) return cudaSuccess;
+  SortView V;
+  cudaError_t e = suffix_sort_core(in, len, out, nb, ws, ws_bytes, sm_count, st, launches, alg_bytes, &V);
+  if (e != cudaSuccess) return e;
+  u32 maxlen = 0;
+  for (int b = 0; b < nb; ++b) maxlen = len[b] > maxlen ? (u32)len[b] : maxlen;
+  u32 gx = (maxlen + 1 + 255) / 256;
+  if (gx > (u32)V.maxg) gx = (u32)V.maxg;
+  if (gx * (u32)nb > (u32)V.maxg * 4u) gx = ((u32)V.maxg * 4u + nb - 1) / nb;
+  if (gx == 0) gx = 1;
+  zpq_bwt_emit<<<dim3(gx, (unsigned)nb), 256, 0, st>>>(V.B, V.txt, V.sa);
+  if (launches) *launches += 1;
+  if (alg_bytes) *alg_bytes += (u64)V.n * 6;
+  return cudaGetLastError();
+}
+
+// The same sort without the BWT: device pointers to the suffix array (slot -> text index), the 1-based ranks (text index ->
+// slot + 1) and the nb + 1 slot offsets, all in the batch's one index space, valid until `ws` is written again (zpq_lz77.cu).
+extern "C" cudaError_t zpq_suffix_arrays(const uint8_t* const* in, const uint64_t* len, int nb, void* ws, uint64_t ws_bytes, int sm_count,
+                                         cudaStream_t st, uint64_t* launches, uint64_t* alg_bytes,
+                                         const uint32_t** sa, const uint32_t** rank, const uint32_t** off) {
+  if (nb <= 0) return cudaSuccess;
+  SortView V;
+  cudaError_t e = suffix_sort_core(in, len, nullptr, nb, ws, ws_bytes, sm_count, st, launches, alg_bytes, &V);
+  if (e != cudaSuccess) return e;
+  *sa = V.sa; *rank = V.rank_of; *off = V.d_off;
+  return cudaSuccess;
 }
 
 // in[b] -> out[b] (DEVICE pointers, host arrays of them), out[b] already holds a copy of in[b]; ws: 3 * nb * 8 bytes of device memory

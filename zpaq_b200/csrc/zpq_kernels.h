@@ -39,6 +39,16 @@ cudaError_t zpq_bwt_forward(const uint8_t* const* in, const uint64_t* len, uint8
 uint64_t zpq_ibwt_workspace(uint64_t total_rows, int nb);
 cudaError_t zpq_bwt_inverse(const uint8_t* const* in, const uint64_t* n, const uint32_t* idx, uint8_t* const* out, int nb,
                             void* ws, uint64_t ws_bytes, int sm_count, cudaStream_t st, uint64_t* launches);
+cudaError_t zpq_suffix_arrays(const uint8_t* const* in, const uint64_t* len, int nb, void* ws, uint64_t ws_bytes, int sm_count,
+                              cudaStream_t st, uint64_t* launches, uint64_t* alg_bytes,
+                              const uint32_t** sa, const uint32_t** rank, const uint32_t** off);
+// zpq_lz77.cu: LZBuffer levels 1 / 2, one thread per block; numbers = makeConfig's $1..$7
+int zpq_lz77_uses_sa(const int numbers[7]);
+uint64_t zpq_lz77_table_bytes(const int numbers[7]);
+uint64_t zpq_lz77_meta_bytes(int nb);
+cudaError_t zpq_lz77_forward(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, const uint64_t* out_cap, int nb,
+                             const int numbers[7], void* tables, const uint32_t* sa, const uint32_t* rank, const uint32_t* base,
+                             void* meta, uint64_t* out_len, int* status, cudaStream_t st, uint64_t* launches);
 cudaError_t zpq_e8e9_forward(const uint8_t* const* in, uint8_t* const* out, const uint64_t* len, int nb, void* ws,
                              int sm_count, cudaStream_t st, uint64_t* launches);
 unsigned long long zpq_code2_signature(const ZFast* F);
