@@ -25,7 +25,7 @@ assert nb == 2 and out == O.gen_block(1, 7, 1800) + O.gen_block(3, 8, 900)
 assert ctx.launch_count() > 0
 ctx.close()
 
-# pre-processing kernels (zpq_bwt.cu): BWT, E8E9 + BWT, E8E9 + CM against blocks written by the unmodified reference
+# pre-processing kernels (zpq_bwt.cu, zpq_lz77.cu): BWT, E8E9, LZ77, store against blocks written by the unmodified reference
 import hashlib
 import json
 import os
@@ -35,8 +35,10 @@ from util import transform_payload
 gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "transforms.json")))["cases"]
 ctx = Z.Context(0)
 by_method = {}
+PRE = {"x0,3ci1": 12000, "x0,7ci1": 12000, "x5,3ci1": 12000, "x5,7ci1": 12000, "x0,4ci1,1,1,1,2am": 12000,        # BWT, E8E9
+       "0": 9000, "x0,0": 70000, "1": 30000, "x0,2,4,0,3,20": 20000, "x0,6,8,0,3,18c0,0,511": 20000, "2": 30000}     # store, LZ77 (hash, suffix array)
 for c in gold:
-    if c["n"] <= 12000:
+    if c["n"] <= PRE.get(c["method"], -1):
         by_method.setdefault(c["method"], []).append(c)
 nt = 0
 for method, cs in by_method.items():

@@ -1,5 +1,5 @@
-"""GPU parity for the pre-processing kernels (zpq_bwt.cu): zpq_compress_blocks with a BWT / E8E9 method must write the
-bytes libzpaq::compressBlock writes (LZBuffer level 3 + e8e9 + makeConfig's PCOMP, libzpaq.cpp:6450-6658, 7135-7323)."""
+"""GPU parity for the pre-processing kernels (zpq_bwt.cu, zpq_lz77.cu): zpq_compress_blocks with a store / LZ77 / BWT / E8E9 method
+must write the bytes libzpaq::compressBlock writes (LZBuffer + e8e9 + makeConfig's PCOMP, libzpaq.cpp:6450-6883, 6920-7323)."""
 import hashlib
 
 import pytest
@@ -55,6 +55,22 @@ def test_full_size_batch_against_the_live_reference(ctx):
     want = b"".join(pays[:5]) + e + big
     out, nb = ctx.decompress_archive(b"".join(blocks[:5]) + be + bb, len(want))
     assert nb == 7 and out == want
+
+
+def test_lz77_batch_against_the_live_reference(ctx):
+    """32 blocks x 256 KiB through the LZ77 parsers (one GPU thread per block): hash-table search with variable-length codes
+    (`1`), suffix-array search (`2`: the batch is suffix-sorted by the BWT's sorter first), byte codes under a model (`3,100,0`),
+    and stored blocks (`1,5,0`); the first and the last block of each against the unmodified reference, all decoded again."""
+    import refpy as R
+    n = 1 << 18
+    pays = [O.gen_block(k % 4, 9000 + k, n - 37 * k) for k in range(32)]
+    for method in ("1", "2", "3,100,0", "1,5,0"):
+        blocks = ctx.compress_blocks(method, pays)
+        if R.available():
+            for k in (0, 31):
+                assert blocks[k] == R.compress_block(pays[k], method), (method, k)
+        out, nb = ctx.decompress_archive(b"".join(blocks), sum(len(p) for p in pays))
+        assert nb == 32 and out == b"".join(pays), method
 
 
 def test_degenerate_payloads(ctx):

@@ -15,7 +15,7 @@ def test_plan_bytes_equal_the_reference(case):
     hdr, prep, prefix = Z.block_plan(case["method"], case["n"])
     assert hdr.hex() == case["header"]
     assert prefix.hex() == case["prefix"]
-    want = case["method"].split(",")[1][:1] if case["method"].startswith("x") else None
+    want = case["method"].split(",")[1][:1] if case["method"].startswith("x") and "," in case["method"] else None
     if want is not None:
         assert prep == int(want)
     assert (prefix[0] == 0) == (prep == 0)
@@ -31,7 +31,7 @@ def test_header_only_entry_point_refuses_transforming_methods():
 
 
 @pytest.mark.parametrize("method", GOLD["rejected"])
-def test_lz77_methods_are_refused(method):
+def test_methods_libzpaq_refuses_are_refused(method):
     with pytest.raises(Z.ZpqError) as e:
         Z.block_plan(method, 20000)
     assert e.value.rc == -13

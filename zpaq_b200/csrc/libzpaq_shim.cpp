@@ -173,7 +173,11 @@ int probe_method(const char* method, const uint8_t* data, uint64_t n, uint8_t* h
     int prep = 0, plen = 0;
     const int32_t g[2] = {0, 0};
     const int rp = zpq_block_plan(method, n, g, hdr, cap, hlen, &prep, prefix, (int)sizeof(prefix), &plen);
-    if (rp == ZPQ_OK && prep != 0) rc = ZPQ_OK;
+    // BWT (3, 7) and E8E9 in front of a context model (4) run on the device at batch speed.  The LZ77 parsers (1, 2, 5, 6) are
+    // built too, but they are sequential per block (one GPU thread each): for zpaq's 16 MiB default blocks and its small
+    // index blocks libzpaq's own parser is the better choice, so they stay there unless ZPQ_SHIM_LZ77=1 asks for the library
+    static const bool lz_too = [] { const char* e = getenv("ZPQ_SHIM_LZ77"); return e && atoi(e) != 0; }();
+    if (rp == ZPQ_OK && prep != 0 && (lz_too || (prep & 3) == 3 || prep == 4)) rc = ZPQ_OK;
   }
   return rc;
 }
