@@ -1249,58 +1249,148 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
       std::vector<size_t> progs;
       for (size_t i = 0; i < nb; ++i)
         if (jobs[i].status == ZPQ_OK && jobs[i].out_len >= 1 && tmp[i][0] == 1) { is_prog[i] = 1; progs.push_back(i); }
-      // Blocks whose program is the plain BWT post-processor (what zpq_compress_blocks / libzpaq write for "x..,3..." methods)
-      // are inverted on the device: LF mapping by a stable radix sort, list ranking by pointer jumping (zpq_bwt.cu).
-      // Every other program runs in the host ZPAQL machine below.
+      // Blocks whose program is one of the post-processors libzpaq's compressBlock (and this library) writes are post-processed
+      // on the device: the BWT inverse as an LF mapping by stable radix sort + list ranking (zpq_bwt.cu), the LZ77 decoders and
+      // the E8E9 inverse with one thread per block (zpq_lz77.cu).  Every other program, a block without a usable size hint,
+      // and any stream those kernels refuse run in the host ZPAQL machine below.
       {
-        std::vector<size_t> bw; std::vector<uint64_t> bn; std::vector<uint32_t> bidx; std::vector<size_t> bskip;
+        struct Rec { size_t i; int kind; size_t skip; uint64_t m; uint64_t n; uint32_t idx; int min_match; };
+        std::vector<Rec> recs;
         const char* he = getenv("ZPQ_HOST_IBWT");                          // A/B switch: 1 = every program in the host machine
         const bool host_only = he && atoi(he) != 0;
         for (size_t i : progs) {
           if (host_only) break;
           const IJob& J = jobs[i];
           const int ph = J.hdr[4], pm = J.hdr[5];
-          if (ph != pm || ph < 20 || ph > 31 || J.seg_out.size() != 1) continue;
-          std::vector<uint8_t> code, pre;
-          if (pcomp_program(3, ph - 20, 0, &code) != ZPQ_OK) continue;
-          pcomp_prefix(code, &pre);
-          if (J.out_len < pre.size() + 6 || memcmp(tmp[i].data(), pre.data(), pre.size()) != 0) continue;
-          const uint64_t n = J.out_len - pre.size() - 5;
-          if (n + 5 > ((uint64_t)1 << pm)) continue;
-          const uint8_t* t = tmp[i].data() + pre.size() + n + 1;
-          const uint32_t ix = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
-          if (ix < 1 || ix > n) continue;
-          bw.push_back(i); bn.push_back(n); bidx.push_back(ix); bskip.push_back(pre.size());
+          if (J.seg_out.size() != 1 || J.out_len < 3) continue;
+          const size_t plen = 3 + (size_t)tmp[i][1] + 256 * (size_t)tmp[i][2];
+          if (J.out_len < plen) continue;
+          int cand[4] = {0, 0, 0, 0}, nc = 0, sc = 0;
+          if (ph == pm && ph >= 20 && ph <= 31) { cand[0] = 3; cand[1] = 7; nc = 2; sc = ph - 20; }
+          else if (ph == 0 && pm >= 20 && pm <= 31) { cand[0] = 1; cand[1] = 5; cand[2] = 2; cand[3] = 6; nc = 4; sc = pm - 20; }
+          else if (ph == 0 && pm == 0) { cand[0] = 4; nc = 1; }
+          for (int c = 0; c < nc; ++c) {
+            const int kind = cand[c];
+            int mm = 0;
+            std::vector<uint8_t> code, pre;
+            if ((kind & 3) == 2) {
+              // the minimum match length is an immediate of the program: find where, read it, rebuild the program with it
+              std::vector<uint8_t> c1, c2;
+              if (pcomp_program(kind, sc, 1, &c1) != ZPQ_OK || pcomp_program(kind, sc, 2, &c2) != ZPQ_OK || c1.size() != c2.size()) continue;
+              size_t at = 0;
+              while (at < c1.size() && c1[at] == c2[at]) ++at;
+              if (at >= c1.size() || 3 + at >= plen) continue;
+              mm = tmp[i][3 + at];
+              if (mm < 1) continue;
+            }
+            if (pcomp_program(kind, sc, mm, &code) != ZPQ_OK) continue;
+            pcomp_prefix(code, &pre);
+            if (pre.size() != plen || memcmp(tmp[i].data(), pre.data(), plen) != 0) continue;
+            Rec r; r.i = i; r.kind = kind; r.skip = plen; r.m = J.out_len - plen; r.n = 0; r.idx = 0; r.min_match = mm;
+            if ((kind & 3) == 3) {
+              if (r.m < 6) break;
+              r.n = r.m - 5;
+              if (r.n + 5 > ((uint64_t)1 << pm)) break;
+              const uint8_t* t = tmp[i].data() + plen + r.n + 1;
+              r.idx = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+              if (r.idx < 1 || r.idx > r.n) break;
+            }
+            else if (kind == 4) r.n = r.m;
+            else {
+              if (hint[i] < 0 || (uint64_t)hint[i] + 4096 > ((uint64_t)1 << pm)) break;     // the decoders need the size up front
+              r.n = (uint64_t)hint[i];
+            }
+            recs.push_back(r);
+            break;
+          }
         }
+        // ---- BWT blocks (3, 7): inverse on the device, E8E9 undone in place for 7 ----
         size_t k = 0;
+        std::vector<Rec> bw, lz;
+        for (const Rec& r : recs) ((r.kind & 3) == 3 ? bw : lz).push_back(r);
         while (k < bw.size()) {
           uint64_t sum = 0; size_t e2 = k;
-          while (e2 < bw.size() && e2 - k < 60000 && (e2 == k || sum + bn[e2] + 1 <= ((uint64_t)1 << 28))) sum += bn[e2++] + 1;
+          while (e2 < bw.size() && e2 - k < 60000 && (e2 == k || sum + bw[e2].n + 1 <= ((uint64_t)1 << 28))) sum += bw[e2++].n + 1;
+          const int cnt = (int)(e2 - k);
           uint64_t bytes = 0;
-          std::vector<uint64_t> o_in(e2 - k), o_out(e2 - k);
-          for (size_t j = k; j < e2; ++j) { o_in[j - k] = bytes; bytes = align_up(bytes + bn[j] + 5 + 16, 256); o_out[j - k] = bytes; bytes = align_up(bytes + bn[j] + 16, 256); }
-          const uint64_t need = zpq_ibwt_workspace(sum, (int)(e2 - k));
-          if (ctx->d_xform.reserve(bytes + 256) == cudaSuccess && ctx->d_xws.reserve(need) == cudaSuccess) {
+          std::vector<uint64_t> o_in(cnt), o_out(cnt), bn(cnt); std::vector<uint32_t> bidx(cnt);
+          for (size_t j = k; j < e2; ++j) {
+            o_in[j - k] = bytes; bytes = align_up(bytes + bw[j].n + 5 + 16, 256); o_out[j - k] = bytes; bytes = align_up(bytes + bw[j].n + 16, 256);
+            bn[j - k] = bw[j].n; bidx[j - k] = bw[j].idx;
+          }
+          const uint64_t need = std::max<uint64_t>(zpq_ibwt_workspace(sum, cnt), zpq_unlz_meta_bytes(cnt));
+          if (sum < ((uint64_t)1 << 31) && ctx->d_xform.reserve(bytes + 256) == cudaSuccess && ctx->d_xws.reserve(need) == cudaSuccess) {
             uint8_t* dx = (uint8_t*)ctx->d_xform.p;
             std::vector<const uint8_t*> pin; std::vector<uint8_t*> pout;
             for (size_t j = k; j < e2; ++j) {
-              const size_t i = bw[j];
-              CK(cudaMemcpyAsync(dx + o_in[j - k], tmp[i].data() + bskip[j], bn[j] + 5, cudaMemcpyHostToDevice, ctx->stream), "H2D BWT rows");
+              const size_t i = bw[j].i;
+              CK(cudaMemcpyAsync(dx + o_in[j - k], tmp[i].data() + bw[j].skip, bw[j].n + 5, cudaMemcpyHostToDevice, ctx->stream), "H2D BWT rows");
               pin.push_back(dx + o_in[j - k]); pout.push_back(dx + o_out[j - k]);
             }
-            CK(zpq_bwt_inverse(pin.data(), bn.data() + k, bidx.data() + k, pout.data(), (int)(e2 - k), ctx->d_xws.p, ctx->d_xws.cap,
+            CK(zpq_bwt_inverse(pin.data(), bn.data(), bidx.data(), pout.data(), cnt, ctx->d_xws.p, ctx->d_xws.cap,
                                ctx->sm_count, ctx->stream, &ctx->launches), "inverse BWT kernels");
+            // E8E9 + BWT blocks: the operands are made relative again where they lie
+            {
+              std::vector<const uint8_t*> ein; std::vector<uint8_t*> eout; std::vector<uint64_t> elen;
+              for (size_t j = k; j < e2; ++j) if (bw[j].kind == 7) { ein.push_back(pout[j - k]); eout.push_back(pout[j - k]); elen.push_back(bw[j].n); }
+              if (!ein.empty()) {
+                std::vector<uint64_t> ol(ein.size()); std::vector<int> os(ein.size());
+                CK(zpq_unlz_forward(ein.data(), elen.data(), eout.data(), elen.data(), (int)ein.size(), 4, 1, 0, 0, ctx->d_xws.p, ol.data(), os.data(),
+                                    ctx->stream, &ctx->launches), "zpq_unlz_kernel launch");
+              }
+            }
             for (size_t j = k; j < e2; ++j) {
-              const size_t i = bw[j];
-              post[i].resize(bn[j]);
-              CK(cudaMemcpyAsync(post[i].data(), pout[j - k], bn[j], cudaMemcpyDeviceToHost, ctx->stream), "D2H inverse BWT");
-              post_seg[i].assign(1, bn[j]);
+              const size_t i = bw[j].i;
+              post[i].resize(bw[j].n);
+              CK(cudaMemcpyAsync(post[i].data(), pout[j - k], bw[j].n, cudaMemcpyDeviceToHost, ctx->stream), "D2H inverse BWT");
+              post_seg[i].assign(1, bw[j].n);
             }
             CK(cudaStreamSynchronize(ctx->stream), "inverse BWT");
-            for (size_t j = k; j < e2; ++j) is_prog[bw[j]] = 2;            // done on the device
+            for (size_t j = k; j < e2; ++j) is_prog[bw[j].i] = 2;          // done on the device
           }
           else cudaGetLastError();                                        // no room: these blocks take the host machine
           k = e2;
+        }
+        // ---- LZ77 decoders (1, 2, 5, 6) and E8E9 alone (4): groups with the same program parameters ----
+        std::vector<char> done(lz.size(), 0);
+        for (size_t a = 0; a < lz.size(); ++a) {
+          if (done[a]) continue;
+          std::vector<size_t> g;
+          const int sc_a = jobs[lz[a].i].hdr[5] >= 20 ? jobs[lz[a].i].hdr[5] - 20 : 0;
+          for (size_t b2 = a; b2 < lz.size(); ++b2) {
+            const int sc_b = jobs[lz[b2].i].hdr[5] >= 20 ? jobs[lz[b2].i].hdr[5] - 20 : 0;
+            if (!done[b2] && lz[b2].kind == lz[a].kind && lz[b2].min_match == lz[a].min_match && sc_b == sc_a) { g.push_back(b2); done[b2] = 1; }
+          }
+          for (size_t k2 = 0; k2 < g.size(); k2 += 4096) {
+            const int cnt = (int)std::min<size_t>(4096, g.size() - k2);
+            uint64_t bytes = 0;
+            std::vector<uint64_t> o_in(cnt), o_out(cnt), ilen(cnt), ocap(cnt), ol(cnt, 0); std::vector<int> os(cnt, 1);
+            for (int j = 0; j < cnt; ++j) {
+              const Rec& r = lz[g[k2 + j]];
+              o_in[j] = bytes; bytes = align_up(bytes + r.m + 16, 256); o_out[j] = bytes; bytes = align_up(bytes + r.n + 16, 256);
+              ilen[j] = r.m; ocap[j] = r.n;
+            }
+            if (ctx->d_xform.reserve(bytes + 256) != cudaSuccess || ctx->d_xws.reserve(zpq_unlz_meta_bytes(cnt)) != cudaSuccess) { cudaGetLastError(); continue; }
+            uint8_t* dx = (uint8_t*)ctx->d_xform.p;
+            std::vector<const uint8_t*> pin; std::vector<uint8_t*> pout;
+            for (int j = 0; j < cnt; ++j) {
+              const Rec& r = lz[g[k2 + j]];
+              if (r.m) CK(cudaMemcpyAsync(dx + o_in[j], tmp[r.i].data() + r.skip, r.m, cudaMemcpyHostToDevice, ctx->stream), "H2D LZ77 codes");
+              pin.push_back(dx + o_in[j]); pout.push_back(dx + o_out[j]);
+            }
+            const int kind = lz[a].kind, base_kind = kind == 4 ? 4 : (kind & 3), e8 = kind >= 4 ? 1 : 0;
+            CK(zpq_unlz_forward(pin.data(), ilen.data(), pout.data(), ocap.data(), cnt, base_kind, e8, sc_a > 4 ? sc_a - 4 : 0, lz[a].min_match,
+                                ctx->d_xws.p, ol.data(), os.data(), ctx->stream, &ctx->launches), "zpq_unlz_kernel launch");
+            for (int j = 0; j < cnt; ++j) {
+              const Rec& r = lz[g[k2 + j]];
+              if (os[j] != 0 || ol[j] != r.n) continue;                   // refused, or not the announced size: the host machine decides
+              post[r.i].resize(r.n);
+              if (r.n) CK(cudaMemcpyAsync(post[r.i].data(), pout[j], r.n, cudaMemcpyDeviceToHost, ctx->stream), "D2H LZ77 output");
+              post_seg[r.i].assign(1, r.n);
+              is_prog[r.i] = 2;
+            }
+            CK(cudaStreamSynchronize(ctx->stream), "LZ77 decode");
+          }
         }
         std::vector<size_t> rest;
         for (size_t i : progs) if (is_prog[i] != 2) rest.push_back(i);

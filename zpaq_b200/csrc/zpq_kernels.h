@@ -49,6 +49,10 @@ uint64_t zpq_lz77_meta_bytes(int nb);
 cudaError_t zpq_lz77_forward(const uint8_t* const* in, const uint64_t* len, uint8_t* const* out, const uint64_t* out_cap, int nb,
                              const int numbers[7], void* tables, const uint32_t* sa, const uint32_t* rank, const uint32_t* base,
                              void* meta, uint64_t* out_len, int* status, cudaStream_t st, uint64_t* launches);
+uint64_t zpq_unlz_meta_bytes(int nb);
+cudaError_t zpq_unlz_forward(const uint8_t* const* in, const uint64_t* in_len, uint8_t* const* out, const uint64_t* out_cap, int nb,
+                             int kind, int e8, int rb, int min_match, void* meta, uint64_t* out_len, int* status,
+                             cudaStream_t st, uint64_t* launches);
 cudaError_t zpq_e8e9_forward(const uint8_t* const* in, uint8_t* const* out, const uint64_t* len, int nb, void* ws,
                              int sm_count, cudaStream_t st, uint64_t* launches);
 unsigned long long zpq_code2_signature(const ZFast* F);

@@ -183,6 +183,99 @@ __global__ void __launch_bounds__(32) zpq_lz77_kernel(const LzBlock* blocks, int
   status[b] = O.full ? 1 : 0;
 }
 
+// ------------------------------------------------------------------ the other direction: what the blocks' PCOMP programs compute
+// One thread per block again (copies depend on what earlier codes wrote).  Anything a well-formed stream cannot contain --
+// an offset before the start of the block, more output than the caller's size hint -- ends the block with status 1 and the
+// host ZPAQL machine takes it, so a damaged archive still behaves as libzpaq's post-processor would.
+struct UnBlock { const u8* in; u8* out; u64 in_len, out_cap; };
+
+// E8E9 inverse: ascending positions, each test on the bytes as they are at that moment (libzpaq.cpp:7296-7320 and the
+// "e8e9 transform to out" passes of the other programs)
+__device__ void un_e8e9(u8* buf, u64 n) {
+  if (n < 5) return;
+  for (u64 i = 0; i + 4 < n; ++i) {
+    if ((buf[i] & 254) == 0xe8 && (((u32)buf[i + 4] + 1u) & 254u) == 0u) {
+      const u32 v = ((u32)buf[i + 1] | (u32)buf[i + 2] << 8 | (u32)buf[i + 3] << 16) - (u32)i;
+      buf[i + 1] = (u8)v; buf[i + 2] = (u8)(v >> 8); buf[i + 3] = (u8)(v >> 16);
+    }
+  }
+}
+
+// kind: 1 = variable-length codes, 2 = byte codes, 4 = E8E9 only (in = the rewritten bytes); e8: undo E8E9 at the end
+__global__ void __launch_bounds__(32) zpq_unlz_kernel(const UnBlock* blocks, int nb, int kind, int e8, u32 rb, u32 min_match, u64* out_len, int* status) {
+  const int b = blockIdx.x;
+  if (b >= nb || threadIdx.x != 0) return;
+  const UnBlock B = blocks[b];
+  const u8* __restrict__ in = B.in;
+  u8* out = B.out;
+  u64 ptr = 0;
+  bool bad = false;
+  if (kind == 4) {
+    if (B.in_len > B.out_cap) bad = true;
+    else { if (B.in != B.out) for (u64 k = 0; k < B.in_len; ++k) out[k] = B.in[k]; ptr = B.in_len; }      // in == out: E8E9 undone in place
+  }
+  else if (kind == 1) {
+    u64 bits = 0; u32 n = 0, state = 0, len = 0, m = 0, r5 = 0;
+    for (u64 k = 0; k < B.in_len && !bad; ++k) {
+      bits += (u64)in[k] << n; n += 8;
+      if (n > 40) { bad = true; break; }
+      if (state == 0) {
+        len = 1;
+        if (bits & 3) { m = (((u32)bits & 3u) - 1u) * 8u; bits >>= 2; m += (u32)bits & 7u; bits >>= 3; n -= 5; state = 1; }
+        else { bits >>= 2; n -= 2; state = 3; }
+      }
+      while (state == 1 && n >= 3) {
+        if (bits & 1) { bits >>= 1; len += len + ((u32)bits & 1u); bits >>= 1; n -= 2; }
+        else { bits >>= 1; len = (len << 2) + ((u32)bits & 3u); bits >>= 2; n -= 3; state = rb ? 5u : 2u; }
+      }
+      if (rb && state == 5 && n >= rb) { r5 = (u32)bits & ((1u << rb) - 1u); bits >>= rb; n -= rb; state = 2; }
+      if (state == 2 && m <= n) {
+        u64 off = (bits & (((u64)1 << m) - 1)) + ((u64)1 << m);
+        if (rb) off = (off << rb) + r5 - ((1u << rb) - 1u);
+        if (off > ptr || off == 0 || ptr + len > B.out_cap) { bad = true; break; }
+        for (u32 j = 0; j < len; ++j) { out[ptr] = out[ptr - off]; ++ptr; }
+        bits >>= m; n -= m; state = 0;
+      }
+      while (state == 3 && n >= 2) {
+        if (bits & 1) { bits >>= 1; len += len + ((u32)bits & 1u); bits >>= 1; n -= 2; }
+        else { bits >>= 1; n -= 1; state = 4; }
+      }
+      if (state == 4 && n >= 8) {
+        if (ptr >= B.out_cap) { bad = true; break; }
+        out[ptr++] = (u8)bits; bits >>= 8; n -= 8;
+        if (--len == 0) state = 0;
+      }
+    }
+  }
+  else {
+    u32 d = 0, len = 0; u64 off = 0;
+    for (u64 k = 0; k < B.in_len && !bad; ++k) {
+      const u32 c = in[k];
+      if (d == 0) {
+        d = (c >> 6) + 1;
+        if (d == 1) len = c + 1;
+        else { ++d; len = (c & 63u) + min_match; }
+        off = 0;
+      }
+      else if (d == 1) {
+        if (ptr >= B.out_cap) { bad = true; break; }
+        out[ptr++] = (u8)c;
+        if (--len == 0) d = 0;
+      }
+      else if (d > 2) { off = (off << 8) | c; --d; }
+      else {
+        off = ((off << 8) | c) + 1;
+        if (off > ptr || ptr + len > B.out_cap || len == 0) { bad = true; break; }
+        for (u32 j = 0; j < len; ++j) { out[ptr] = out[ptr - off]; ++ptr; }
+        d = 0;
+      }
+    }
+  }
+  if (!bad && e8) un_e8e9(out, ptr);
+  out_len[b] = ptr;
+  status[b] = bad ? 1 : 0;
+}
+
 inline u64 al256(u64 x) { return (x + 255) & ~(u64)255; }
 
 }  // namespace
@@ -243,3 +336,31 @@ extern "C" cudaError_t zpq_lz77_forward(const uint8_t* const* in, const uint64_t
 }
 
 extern "C" uint64_t zpq_lz77_meta_bytes(int nb) { return al256((u64)nb * sizeof(LzBlock)) + al256((u64)nb * 8) + al256((u64)nb * 4) + 256; }
+
+// Post-processing of blocks whose program is one this library writes: kind 1 / 2 = LZ77 decoders, 4 = E8E9 only, e8 = undo E8E9
+// after the decode; in[b]: the model bytes after the program (DEVICE pointers, host arrays), out[b]: out_cap[b] bytes.
+// meta: zpq_unlz_meta_bytes(nb) of device memory.  out_len / status (host) are valid on return; status 1 = not a stream this
+// kernel takes (the caller falls back to the host ZPAQL machine).
+extern "C" uint64_t zpq_unlz_meta_bytes(int nb) { return al256((u64)nb * sizeof(UnBlock)) + al256((u64)nb * 8) + al256((u64)nb * 4) + 256; }
+
+extern "C" cudaError_t zpq_unlz_forward(const uint8_t* const* in, const uint64_t* in_len, uint8_t* const* out, const uint64_t* out_cap, int nb,
+                                        int kind, int e8, int rb, int min_match, void* meta, uint64_t* out_len, int* status,
+                                        cudaStream_t st, uint64_t* launches) {
+  if (nb <= 0) return cudaSuccess;
+  UnBlock* hb = new UnBlock[nb];
+  for (int b = 0; b < nb; ++b) { hb[b].in = in[b]; hb[b].out = out[b]; hb[b].in_len = in_len[b]; hb[b].out_cap = out_cap[b]; }
+  u8* dm = (u8*)meta;
+  UnBlock* d_blocks = (UnBlock*)dm;
+  u64* d_len = (u64*)(dm + al256((u64)nb * sizeof(UnBlock)));
+  int* d_st = (int*)(dm + al256((u64)nb * sizeof(UnBlock)) + al256((u64)nb * 8));
+  cudaError_t e = cudaMemcpyAsync(d_blocks, hb, (size_t)nb * sizeof(UnBlock), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  delete[] hb;
+  if (e != cudaSuccess) return e;
+  zpq_unlz_kernel<<<nb, 32, 0, st>>>(d_blocks, nb, kind, e8, (u32)rb, (u32)min_match, d_len, d_st);
+  if (launches) *launches += 1;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(out_len, d_len, (size_t)nb * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(status, d_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+  return cudaStreamSynchronize(st);
+}
