@@ -1346,7 +1346,15 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
               post_seg[i].assign(1, bw[j].n);
             }
             CK(cudaStreamSynchronize(ctx->stream), "inverse BWT");
-            for (size_t j = k; j < e2; ++j) is_prog[bw[j].i] = 2;          // done on the device
+            for (size_t j = k; j < e2; ++j) {
+              const size_t i = bw[j].i;
+              is_prog[i] = 2;                                             // done on the device
+              if (bw[j].kind == 7 && bv[i].segs[0].has_sha1) {            // E8E9 undone by zpq_unlz_kernel: same cross-check as below
+                uint8_t dg[20];
+                sha1_of(post[i].data(), post[i].size(), dg);
+                if (memcmp(dg, bv[i].segs[0].sha1, 20) != 0) { is_prog[i] = 1; post[i].clear(); post_seg[i].clear(); }
+              }
+            }
           }
           else cudaGetLastError();                                        // no room: these blocks take the host machine
           k = e2;
@@ -1390,6 +1398,15 @@ int zpq_decompress_archive(zpq_ctx* ctx, const uint8_t* arc, uint64_t arc_len, u
               is_prog[r.i] = 2;
             }
             CK(cudaStreamSynchronize(ctx->stream), "LZ77 decode");
+            // a block that carries its checksum is checked here: if the device decoder and the checksum disagree the host
+            // machine gets the block (it then either agrees with the checksum or the archive really is damaged)
+            for (int j = 0; j < cnt; ++j) {
+              const Rec& r = lz[g[k2 + j]];
+              if (is_prog[r.i] != 2 || !bv[r.i].segs[0].has_sha1) continue;
+              uint8_t dg[20];
+              sha1_of(post[r.i].data(), post[r.i].size(), dg);
+              if (memcmp(dg, bv[r.i].segs[0].sha1, 20) != 0) { is_prog[r.i] = 1; post[r.i].clear(); post_seg[r.i].clear(); }
+            }
           }
         }
         std::vector<size_t> rest;
