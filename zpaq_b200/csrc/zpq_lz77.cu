@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(32) zpq_lz77_kernel(const LzBlock* blocks, int
   const u32 mask = (1u << C.checkbits) - 1u;
   u32 i = 0, lit = 0, h1 = 0;
   while (i < n) {
-    u32 blen = C.min_match - 1, bp = 0, blit = 0;
-    int bscore = 0;
+    u32 best_len = C.min_match - 1, best_pos = 0, best_back = 0;
+    int best_score = 0;
     if (C.use_sa) {
       // the ISA window of position i: entry x holds the rank of position (i & ~mask) + x once the window was rebuilt for it
       {
@@ -122,20 +122,20 @@ __global__ void __launch_bounds__(32) zpq_lz77_kernel(const LzBlock* blocks, int
         if (B.sa[B.base + q] - B.base != h + i) continue;
         for (int dir = -1; dir <= 1; dir += 2) {
           for (u32 k = 1; k <= C.bucket; ++k) {
-            const u32 qq = q + (u32)(dir * (int)k);
+            const u32 nbr = q + (u32)(dir * (int)k);
             u32 p;
-            if (qq < n && (p = B.sa[B.base + qq] - B.base - h) < i) {
-              u32 l, l1;
-              for (l = h; i + l < n && l < C.max_match && in[p + l] == in[i + l]; ++l) { }
-              for (l1 = h; l1 > 0 && in[p + l1 - 1] == in[i + l1 - 1]; --l1) { }
-              int score = (int)(l - l1) * 8 - lz_lg(i - p) - 4 * (lit == 0 && l1 > 0 ? 1 : 0) - 11;
+            if (nbr < n && (p = B.sa[B.base + nbr] - B.base - h) < i) {
+              u32 run, back;
+              for (run = h; i + run < n && run < C.max_match && in[p + run] == in[i + run]; ++run) { }
+              for (back = h; back > 0 && in[p + back - 1] == in[i + back - 1]; --back) { }
+              int score = (int)(run - back) * 8 - lz_lg(i - p) - 4 * (lit == 0 && back > 0 ? 1 : 0) - 11;
               for (u32 a = 0; a < h; ++a) score = score * 5 / 8;
-              if (score > bscore) { blen = l; bp = p; blit = l1; bscore = score; }
-              if (l < blen || l < C.min_match || l > 255) break;
+              if (score > best_score) { best_len = run; best_pos = p; best_back = back; best_score = score; }
+              if (run < best_len || run < C.min_match || run > 255) break;
             }
           }
         }
-        if (bscore <= 0 || blen < C.min_match) break;
+        if (best_score <= 0 || best_len < C.min_match) break;
       }
     }
     else if (C.level == 1 || C.min_match <= 64) {
@@ -143,30 +143,30 @@ __global__ void __launch_bounds__(32) zpq_lz77_kernel(const LzBlock* blocks, int
         u32 p = tab[h1 ^ k];
         if (p && i + 3 < n && (p & mask) == ((u32)in[i + 3] & mask)) {
           p >>= C.checkbits;
-          if (p < i && i + blen <= n && in[p + blen - 1] == in[i + blen - 1]) {
-            u32 l;
-            for (l = 0; i + l < n && l < C.max_match && in[p + l] == in[i + l]; ++l) { }
-            const int score = (int)l * 8 - lz_lg(i - p) - 2 * (lit > 0 ? 1 : 0) - 11;
-            if (score > bscore) { blen = l; bp = p; blit = 0; bscore = score; }
+          if (p < i && i + best_len <= n && in[p + best_len - 1] == in[i + best_len - 1]) {
+            u32 run;
+            for (run = 0; i + run < n && run < C.max_match && in[p + run] == in[i + run]; ++run) { }
+            const int score = (int)run * 8 - lz_lg(i - p) - 2 * (lit > 0 ? 1 : 0) - 11;
+            if (score > best_score) { best_len = run; best_pos = p; best_back = 0; best_score = score; }
           }
         }
-        if (blen >= 128) break;
+        if (best_len >= 128) break;
       }
     }
     // a match that pays for its code, else one more literal
-    const u32 off = i - bp;
-    if (off > 0 && bscore > 0 && blen - blit >= C.min_match + (C.level == 2 ? ((off >= (1u << 16)) + (off >= (1u << 24))) : 0u)) {
-      lit += blit;
-      lz_literals(C, O, in, i + blit, lit);
-      lz_match(C, O, blen - blit, off);
+    const u32 off = i - best_pos;
+    if (off > 0 && best_score > 0 && best_len - best_back >= C.min_match + (C.level == 2 ? ((off >= (1u << 16)) + (off >= (1u << 24))) : 0u)) {
+      lit += best_back;
+      lz_literals(C, O, in, i + best_back, lit);
+      lz_match(C, O, best_len - best_back, off);
     } else {
-      blen = 1;
+      best_len = 1;
       ++lit;
     }
     // index what is stepped over
-    if (C.use_sa) i += blen;
+    if (C.use_sa) i += best_len;
     else {
-      while (blen--) {
+      while (best_len--) {
         if (i + C.min_both < n) {
           const u32 ih = ((i * 1234547u) >> 19) & C.bucket;
           tab[h1 ^ ih] = (i << C.checkbits) | ((u32)in[i + 3] & mask);
