@@ -32,8 +32,10 @@ def worker(rank, world, port, libpath, q):
         lens = [len(p) for p in pays]
     arc, alens, tm = shard.compress_sharded(ctx, "5", flat, lens, src=0, device="cpu")
     out, olens, tm2 = shard.decompress_sharded(ctx, arc, src=0, device="cpu")
+    # the same scatter / gather around a method that pre-processes on the device (BWT: suffix sort of each rank's blocks)
+    arc_b, alens_b, _ = shard.compress_sharded(ctx, "x0,3ci1", flat, lens, src=0, device="cpu")
     if rank == 0:
-        q.put((arc.numpy().tobytes(), alens, out.numpy().tobytes(), olens))
+        q.put((arc.numpy().tobytes(), alens, out.numpy().tobytes(), olens, arc_b.numpy().tobytes(), alens_b))
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
@@ -50,7 +52,7 @@ if __name__ == "__main__":
     procs = [c.Process(target=worker, args=(r, 2, port, Z.LIB_PATH, q)) for r in range(2)]
     for p in procs:
         p.start()
-    arc, alens, out, olens = q.get(timeout=600)
+    arc, alens, out, olens, arc_b, alens_b = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -60,4 +62,6 @@ if __name__ == "__main__":
     if refpy.available():
         want = [refpy.compress_block(p, "5") for p in pays]
         assert arc == b"".join(want) and alens == [len(w) for w in want]
+        want_b = [refpy.compress_block(p, "x0,3ci1") for p in pays]
+        assert arc_b == b"".join(want_b) and alens_b == [len(w) for w in want_b]
     print("simt shard ok: %d blocks over 2 ranks, %d archive bytes" % (len(pays), len(arc)))
