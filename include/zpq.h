@@ -142,9 +142,14 @@ int zpq_last_tiers(const zpq_ctx* ctx, uint32_t tiers[7]);
 /* Batched libzpaq::compressBlock (libzpaq.cpp:7543-7731): for each payload
  * writes one complete .zpaq block -- locator tag, "zPQ" header, one segment
  * (filename, comment = decimal size [+ " " + comment]), coded data, SHA-1
- * trailer, end-of-block -- bit-identical to the reference for methods in the
- * context-model family.  out[i] must hold out_cap[i] bytes; out_len[i] returns
- * the block size.  filenames/comments may be NULL. */
+ * trailer, end-of-block -- bit-identical to the reference for every method
+ * compressBlock takes: digit methods "L[B][,R,T]" of levels 0-5 (store, LZ77,
+ * BWT, context mixing, each with E8E9 for exe block types: libzpaq.cpp:7596-7691)
+ * and "x..." methods (makeConfig, 6887-7535), with the pre-processing of
+ * LZBuffer / e8e9() (6450-6883) done on the device.  Not taken: LZ77 with a
+ * second context order ("x..." with $4 > 0) -> ZPQ_E_METHOD.  out[i] must hold
+ * out_cap[i] bytes; out_len[i] returns the block size.  filenames/comments may
+ * be NULL. */
 int zpq_compress_blocks(zpq_ctx* ctx, int nblk, const char* method,
                         const uint8_t* const* data, const uint64_t* len,
                         const char* const* filenames, const char* const* comments, int dosha1,
@@ -165,7 +170,8 @@ int zpq_header_from_stats(const char* method, uint64_t n, const int32_t gaps[2],
  * pre-processing of the payload (makeConfig's second number, libzpaq.cpp:6894: 0 none, 3 BWT, 4 E8E9, 7 E8E9 then BWT --
  * LZBuffer level 3 and e8e9(), libzpaq.cpp:6450-6459, 6649-6658) and the bytes that pass through the model in front of
  * the (transformed) payload: "0" (PASS) or "1, len, PCOMP program" (Compressor::postProcess, libzpaq.cpp:2888-2915).
- * LZ77 methods return ZPQ_E_METHOD. */
+ * prep may also be 1 / 2 (LZ77 with variable-length / byte codes) and 5 / 6 (the same behind E8E9); a header with n = 0
+ * components means the bytes are stored (Encoder::compress without a model, libzpaq.cpp:2436-2445). */
 int zpq_block_plan(const char* method, uint64_t n, const int32_t gaps[2], uint8_t* hdr, int hdr_cap, int* hlen,
                    int* prep, uint8_t* prefix, int prefix_cap, int* prefix_len);
 /* Device-side analysis of payloads in HBM: sha1 = 20 bytes per block (or NULL), gaps = 2 ints per block (the dominant
